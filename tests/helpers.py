@@ -1,0 +1,55 @@
+"""Shared test helpers: analytic occupancy fields, mesh invariants, synthetic `opt`."""
+import hashlib
+import types
+
+import numpy as np
+
+
+def analytic_eval_func(points):
+    """Stand-in for reconstruction()'s eval_func closure (lib/mesh_util.py:20-28): takes float64
+    points [3,n], returns (hr, lr) float32 arrays shaped [1,1,n] like the network's predictions.
+    HR: a bumpy ellipsoid; LR: a smoother, slightly different one (so HR/LR octree masks differ)."""
+    p = np.asarray(points, dtype=np.float32).astype(np.float64)
+    x, y, z = p[0], p[1], p[2]
+    r_hr = np.sqrt((x / 0.30) ** 2 + (y / 0.42) ** 2 + (z / 0.22) ** 2)
+    r_hr = r_hr + 0.06 * np.sin(17.0 * x) * np.cos(13.0 * y) + 0.04 * np.sin(23.0 * z)
+    r_lr = np.sqrt(((x - 0.02) / 0.31) ** 2 + (y / 0.40) ** 2 + ((z + 0.01) / 0.24) ** 2)
+    hr = 1.0 / (1.0 + np.exp((r_hr - 1.0) * 14.0))
+    lr = 1.0 / (1.0 + np.exp((r_lr - 1.0) * 9.0))
+    return (hr.astype(np.float32)[None, None, :], lr.astype(np.float32)[None, None, :])
+
+
+def make_opt(**kw):
+    """The fields of the reference's `opt` that the hot path reads."""
+    d = dict(threshold=0.05, num_samples=50000, resolution=128, loadSize=512, z_size=200.0, num_views=1,
+             mlp_dim_lr=[321, 1024, 512, 256, 128, 1], mlp_dim_hr=[322, 1024, 512, 256, 128, 1],
+             mlp_res_layers_lr=[2, 3, 4], mlp_res_layers_hr=[2, 3, 4], no_residual=False,
+             b_min=[-0.5, -0.5, -0.5], b_max=[0.5, 0.5, 0.5])
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def mesh_euler_closed(verts, faces, closed=True):
+    """Asserts 2-manifoldness with consistent orientation; returns the Euler characteristic."""
+    faces = np.asarray(faces, dtype=np.int64)
+    e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]])
+    n = len(verts) + 1
+    key = e[:, 0] * n + e[:, 1]
+    rkey = e[:, 1] * n + e[:, 0]
+    u, c = np.unique(key, return_counts=True)
+    assert c.max() == 1, "a directed edge is used by two faces (non-manifold / flipped face)"
+    if closed:
+        assert np.array_equal(np.sort(key), np.sort(rkey)), "surface not closed or inconsistently oriented"
+    und = np.unique(np.minimum(key, rkey))
+    return len(verts) - len(und) + len(faces)
+
+
+def sphere_volume(R, radius, sharp=1.5, centre=None):
+    g = np.stack(np.meshgrid(*[np.arange(R)] * 3, indexing="ij")).astype(np.float64)
+    c = (R - 1) / 2 if centre is None else centre
+    r = np.sqrt(((g - c) ** 2).sum(0))
+    return (1.0 / (1.0 + np.exp((r - radius) / sharp))).astype(np.float32)
