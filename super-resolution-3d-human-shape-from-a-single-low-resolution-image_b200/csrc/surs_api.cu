@@ -1,0 +1,420 @@
+// C-ABI entry points of libsurs.so (see include/surs.h for the contract and the
+// reference file:line each one replaces).
+#include "common.cuh"
+
+#include <new>
+#include <stdlib.h>
+
+static char g_create_err[512] = "";
+
+extern "C" int surs_version(void) { return 100; }
+
+int surs_ensure(surs_ctx *ctx, void **ptr, size_t *cap, size_t bytes)
+{
+    if (*cap >= bytes && *ptr) return 0;
+    if (*ptr) SURS_CUDA(ctx, cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    SURS_CUDA(ctx, cudaMalloc(ptr, bytes));
+    *cap = bytes;
+    return 0;
+}
+
+extern "C" int surs_create(surs_ctx **out, int device)
+{
+    if (!out) return 1;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        snprintf(g_create_err, sizeof(g_create_err), "surs_create: no CUDA device %d (%s)", device,
+                 e == cudaSuccess ? "ordinal out of range" : cudaGetErrorString(e));
+        return 1;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) {
+        snprintf(g_create_err, sizeof(g_create_err),
+                 "surs_create: device %d is sm_%d%d; libsurs is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return 1;
+    }
+    surs_ctx *ctx = new (std::nothrow) surs_ctx();
+    if (!ctx) return 1;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaSetDevice(device);
+    if (cudaMalloc(&ctx->counter, 64) != cudaSuccess || surs_mc_init_tables(ctx) != 0) {
+        snprintf(g_create_err, sizeof(g_create_err), "surs_create: device allocation failed: %s", ctx->err);
+        delete ctx;
+        return 1;
+    }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void surs_destroy(surs_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int m = 0; m < 2; ++m)
+        for (int l = 0; l < SURS_NUM_LAYERS; ++l) {
+            cudaFree(ctx->wt32[m][l]);
+            cudaFree(ctx->b32[m][l]);
+        }
+    cudaFree(ctx->tc_weights);
+    cudaFree(ctx->tc_scratch);
+    cudaFree(ctx->f_lr32); cudaFree(ctx->f_hr32); cudaFree(ctx->f_lr16); cudaFree(ctx->f_hr16);
+    cudaFree(ctx->axis_dev); cudaFree(ctx->dirty); cudaFree(ctx->idx_list); cudaFree(ctx->counter);
+    cudaFree(ctx->stage_pts); cudaFree(ctx->stage_out);
+    cudaFree(ctx->mc_block_tot); cudaFree(ctx->mc_vid); cudaFree(ctx->mc_tables);
+    delete ctx;
+}
+
+extern "C" const char *surs_last_error(const surs_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+extern "C" int64_t surs_launch_count(const surs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols)
+{
+    __shared__ float tile[32][33];
+    int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8)
+        if (r0 + i < rows && c < cols) tile[i][threadIdx.x] = src[(size_t)(r0 + i) * cols + c];
+    __syncthreads();
+    int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += 8)
+        if (c0 + i < cols && r < rows) dst[(size_t)(c0 + i) * rows + r] = tile[threadIdx.x][i];
+}
+
+extern "C" int surs_set_weights(surs_ctx *ctx,
+                                const float *const w_lr[SURS_NUM_LAYERS], const float *const b_lr[SURS_NUM_LAYERS],
+                                const float *const w_hr[SURS_NUM_LAYERS], const float *const b_hr[SURS_NUM_LAYERS],
+                                const int dims_lr[SURS_NUM_LAYERS + 1], const int dims_hr[SURS_NUM_LAYERS + 1],
+                                const int *res_layers, int n_res, void *stream)
+{
+    if (!ctx) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    static const int want_lr[6] = {SURS_C0_LR, 1024, 512, 256, 128, 1};
+    static const int want_hr[6] = {SURS_C0_HR, 1024, 512, 256, 128, 1};
+    for (int i = 0; i < 6; ++i)
+        if (dims_lr[i] != want_lr[i] || dims_hr[i] != want_hr[i])
+            SURS_FAIL(ctx, "surs_set_weights: unsupported mlp_dim (kernels are instantiated for 321/322-1024-512-256-128-1)");
+    if (n_res != 3 || res_layers[0] != 2 || res_layers[1] != 3 || res_layers[2] != 4)
+        SURS_FAIL(ctx, "surs_set_weights: unsupported mlp_res_layers (kernels are instantiated for [2,3,4])");
+    const float *const *w[2] = {w_lr, w_hr};
+    const float *const *b[2] = {b_lr, b_hr};
+    const int *dims[2] = {dims_lr, dims_hr};
+    const float *wsrc[2][SURS_NUM_LAYERS];
+    for (int m = 0; m < 2; ++m) {
+        memcpy(ctx->dims[m], dims[m], sizeof(int) * 6);
+        for (int l = 0; l < SURS_NUM_LAYERS; ++l) {
+            const int cout = dims[m][l + 1];
+            const int cin = dims[m][l] + ((l >= 2) ? dims[m][0] : 0);
+            ctx->cin[m][l] = cin;
+            if (!w[m][l] || !b[m][l]) SURS_FAIL(ctx, "surs_set_weights: null parameter pointer");
+            if (!ctx->wt32[m][l]) SURS_CUDA(ctx, cudaMalloc(&ctx->wt32[m][l], sizeof(float) * (size_t)cin * cout));
+            if (!ctx->b32[m][l]) SURS_CUDA(ctx, cudaMalloc(&ctx->b32[m][l], sizeof(float) * cout));
+            dim3 grid((cin + 31) / 32, (cout + 31) / 32), block(32, 8);
+            transpose_kernel<<<grid, block, 0, st>>>(w[m][l], ctx->wt32[m][l], cout, cin);
+            SURS_LAUNCH_CHECK(ctx, "transpose_kernel");
+            SURS_CUDA(ctx, cudaMemcpyAsync(ctx->b32[m][l], b[m][l], sizeof(float) * cout, cudaMemcpyDeviceToDevice, st));
+            wsrc[m][l] = w[m][l];
+        }
+    }
+    if (surs_tc_pack_weights(ctx, wsrc, st)) return 1;
+    SURS_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->have_weights = 1;
+    return 0;
+}
+
+// NCHW fp32 -> NHWC fp32 + fp16.  One block per (pixel tile of 32) x (channel tile of 32).
+__global__ void repack_kernel(const float *__restrict__ src, float *__restrict__ dst32, __half *__restrict__ dst16,
+                              int C, int HW)
+{
+    __shared__ float tile[32][33];
+    int px = blockIdx.x * 32 + threadIdx.x, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8)
+        if (c0 + i < C && px < HW) tile[i][threadIdx.x] = src[(size_t)(c0 + i) * HW + px];
+    __syncthreads();
+    int c = c0 + threadIdx.x, p0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += 8)
+        if (p0 + i < HW && c < C) {
+            float v = tile[threadIdx.x][i];
+            dst32[(size_t)(p0 + i) * C + c] = v;
+            dst16[(size_t)(p0 + i) * C + c] = __float2half_rn(v);
+        }
+}
+
+extern "C" int surs_set_features(surs_ctx *ctx, const float *f_lr, int C_lr, int H_lr, int W_lr,
+                                 const float *f_hr, int C_hr, int H_hr, int W_hr, void *stream)
+{
+    if (!ctx) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (C_lr != SURS_C_LR || C_hr != SURS_C_HR)
+        SURS_FAIL(ctx, "surs_set_features: expected %d + %d channels, got %d + %d", SURS_C_LR, SURS_C_HR, C_lr, C_hr);
+    if (H_lr < 2 || W_lr < 2 || H_hr < 2 || W_hr < 2 || !f_lr || !f_hr)
+        SURS_FAIL(ctx, "surs_set_features: bad feature map shape");
+    const size_t n_lr = (size_t)H_lr * W_lr * C_lr, n_hr = (size_t)H_hr * W_hr * C_hr;
+    if (n_lr > ctx->f_lr_cap) {
+        cudaFree(ctx->f_lr32); cudaFree(ctx->f_lr16); ctx->f_lr32 = nullptr; ctx->f_lr16 = nullptr; ctx->f_lr_cap = 0;
+        SURS_CUDA(ctx, cudaMalloc(&ctx->f_lr32, n_lr * sizeof(float)));
+        SURS_CUDA(ctx, cudaMalloc(&ctx->f_lr16, n_lr * sizeof(__half)));
+        ctx->f_lr_cap = n_lr;
+    }
+    if (n_hr > ctx->f_hr_cap) {
+        cudaFree(ctx->f_hr32); cudaFree(ctx->f_hr16); ctx->f_hr32 = nullptr; ctx->f_hr16 = nullptr; ctx->f_hr_cap = 0;
+        SURS_CUDA(ctx, cudaMalloc(&ctx->f_hr32, n_hr * sizeof(float)));
+        SURS_CUDA(ctx, cudaMalloc(&ctx->f_hr16, n_hr * sizeof(__half)));
+        ctx->f_hr_cap = n_hr;
+    }
+    dim3 block(32, 8);
+    repack_kernel<<<dim3((H_lr * W_lr + 31) / 32, C_lr / 32), block, 0, st>>>(f_lr, ctx->f_lr32, ctx->f_lr16, C_lr, H_lr * W_lr);
+    SURS_LAUNCH_CHECK(ctx, "repack_kernel(lr)");
+    repack_kernel<<<dim3((H_hr * W_hr + 31) / 32, C_hr / 32), block, 0, st>>>(f_hr, ctx->f_hr32, ctx->f_hr16, C_hr, H_hr * W_hr);
+    SURS_LAUNCH_CHECK(ctx, "repack_kernel(hr)");
+    ctx->H_lr = H_lr; ctx->W_lr = W_lr; ctx->H_hr = H_hr; ctx->W_hr = W_hr;
+    ctx->have_features = 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// query
+// ------------------------------------------------------------------------------------
+static int check_ready(surs_ctx *ctx, int precision)
+{
+    if (!ctx->have_weights) SURS_FAIL(ctx, "surs_set_weights has not been called");
+    if (!ctx->have_features) SURS_FAIL(ctx, "surs_set_features has not been called");
+    if (precision != SURS_PREC_FP32 && precision != SURS_PREC_FP16) SURS_FAIL(ctx, "unknown precision %d", precision);
+    return 0;
+}
+
+static int run_query(surs_ctx *ctx, const PointIO &io, int precision, cudaStream_t st)
+{
+    return precision == SURS_PREC_FP32 ? surs_launch_query_simt(ctx, io, st) : surs_launch_query_tc(ctx, io, st);
+}
+
+static void fill_proj(PointIO &io, const float calib[12], float z_num, float z_den)
+{
+    memcpy(io.calib, calib, sizeof(float) * 12);
+    io.z_num = z_num;
+    io.z_den = z_den;
+}
+
+extern "C" int surs_query(surs_ctx *ctx, const float *pts, int64_t n, const float calib[12],
+                          float z_num, float z_den, int precision, float *pred_hr, float *pred_lr, void *stream)
+{
+    if (!ctx) return 1;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (check_ready(ctx, precision)) return 1;
+    if (n < 0 || (n > 0 && (!pts || !pred_hr || !pred_lr))) SURS_FAIL(ctx, "surs_query: bad arguments");
+    PointIO io;
+    memset(&io, 0, sizeof(io));
+    io.pts = pts; io.n = n; io.out_hr = pred_hr; io.out_lr = pred_lr;
+    fill_proj(io, calib, z_num, z_den);
+    return run_query(ctx, io, precision, (cudaStream_t)stream);
+}
+
+extern "C" int surs_query_host(surs_ctx *ctx, const float *pts_host, int64_t n, const float calib[12],
+                               float z_num, float z_den, int precision,
+                               float *pred_hr_host, float *pred_lr_host, void *stream)
+{
+    if (!ctx) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n <= 0) return n < 0;
+    size_t need = sizeof(float) * 3 * (size_t)n;
+    if (need > ctx->stage_cap) {
+        cudaFree(ctx->stage_pts); cudaFree(ctx->stage_out); ctx->stage_pts = ctx->stage_out = nullptr; ctx->stage_cap = 0;
+        SURS_CUDA(ctx, cudaMalloc(&ctx->stage_pts, need));
+        SURS_CUDA(ctx, cudaMalloc(&ctx->stage_out, sizeof(float) * 2 * (size_t)n));
+        ctx->stage_cap = need;
+    }
+    SURS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_pts, pts_host, need, cudaMemcpyHostToDevice, st));
+    if (surs_query(ctx, ctx->stage_pts, n, calib, z_num, z_den, precision, ctx->stage_out, ctx->stage_out + n, stream)) return 1;
+    SURS_CUDA(ctx, cudaMemcpyAsync(pred_hr_host, ctx->stage_out, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    SURS_CUDA(ctx, cudaMemcpyAsync(pred_lr_host, ctx->stage_out + n, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    SURS_CUDA(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// grid evaluation
+// ------------------------------------------------------------------------------------
+// lib/sdf.py:17-24: coords = diag(len/res) @ idx + b_min in float64 (product rounded, then sum rounded).
+static int setup_grid(surs_ctx *ctx, PointIO &io, const int res[3], const double b_min[3], const double b_max[3],
+                      const double *transform, cudaStream_t st)
+{
+    if (res[0] < 1 || res[1] < 1 || res[2] < 1) SURS_FAIL(ctx, "bad grid resolution");
+    const size_t total = (size_t)res[0] + res[1] + res[2];
+    if (surs_ensure(ctx, (void **)&ctx->axis_dev, &ctx->axis_cap, total * sizeof(double))) return 1;
+    double *host = (double *)malloc(total * sizeof(double));
+    if (!host) SURS_FAIL(ctx, "out of host memory");
+    size_t o = 0;
+    for (int a = 0; a < 3; ++a) {
+        volatile double step = (b_max[a] - b_min[a]) / (double)res[a];
+        io.axis[a] = ctx->axis_dev + o;
+        for (int i = 0; i < res[a]; ++i) {
+            volatile double prod = step * (double)i;     // volatile: no FMA contraction, as numpy
+            host[o + i] = prod + b_min[a];
+        }
+        o += res[a];
+    }
+    cudaError_t e = cudaMemcpyAsync(ctx->axis_dev, host, total * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // host buffer is pageable and freed below
+    free(host);
+    if (e != cudaSuccess) SURS_FAIL(ctx, "axis table upload failed: %s", cudaGetErrorString(e));
+    io.grid = 1;
+    io.R1 = res[1];
+    io.R2 = res[2];
+    io.has_T = transform != nullptr;
+    if (transform) memcpy(io.T, transform, sizeof(double) * 12);
+    return 0;
+}
+
+extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_min[3], const double b_max[3],
+                              const double *transform, const float calib[12], float z_num, float z_den,
+                              int precision, int plane_lo, int plane_hi, float *sdf_hr, float *sdf_lr, void *stream)
+{
+    if (!ctx) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (check_ready(ctx, precision)) return 1;
+    if (plane_lo < 0 || plane_hi > res[0] || plane_lo >= plane_hi) SURS_FAIL(ctx, "surs_eval_grid: bad slab [%d,%d)", plane_lo, plane_hi);
+    PointIO io;
+    memset(&io, 0, sizeof(io));
+    if (setup_grid(ctx, io, res, b_min, b_max, transform, st)) return 1;
+    fill_proj(io, calib, z_num, z_den);
+    const int64_t plane = (int64_t)res[1] * res[2];
+    io.lin_base = plane * plane_lo;
+    io.n = plane * (plane_hi - plane_lo);
+    // outputs are slab-relative: out[n]
+    io.out_hr = sdf_hr;
+    io.out_lr = sdf_lr;
+    // one launch handles < 2^31 CTAs; split very large slabs
+    const int64_t chunk = (int64_t)1 << 30;
+    for (int64_t s = 0; s < io.n; s += chunk) {
+        PointIO part = io;
+        part.lin_base = io.lin_base + s;
+        part.n = (io.n - s < chunk) ? io.n - s : chunk;
+        part.out_hr = sdf_hr + s;
+        part.out_lr = sdf_lr + s;
+        if (run_query(ctx, part, precision, st)) return 1;
+    }
+    return 0;
+}
+
+// octree kernels live in grid.cu
+int surs_octree_select_impl(surs_ctx *ctx, const int res[3], int reso, uint8_t *dirty, int64_t *idx,
+                            int64_t *n_selected, cudaStream_t st);
+int surs_octree_cells_impl(surs_ctx *ctx, const int res[3], int reso, double threshold, double *sdf_hr,
+                           double *sdf_lr, uint8_t *dirty, cudaStream_t st);
+
+extern "C" int surs_octree_select(surs_ctx *ctx, const int res[3], int reso, uint8_t *dirty, int64_t *idx,
+                                  int64_t *n_selected, void *stream)
+{
+    if (!ctx) return 1;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return surs_octree_select_impl(ctx, res, reso, dirty, idx, n_selected, (cudaStream_t)stream);
+}
+
+extern "C" int surs_octree_cells(surs_ctx *ctx, const int res[3], int reso, double threshold, double *sdf_hr,
+                                 double *sdf_lr, uint8_t *dirty, void *stream)
+{
+    if (!ctx) return 1;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return surs_octree_cells_impl(ctx, res, reso, threshold, sdf_hr, sdf_lr, dirty, (cudaStream_t)stream);
+}
+
+extern "C" int surs_eval_grid_octree(surs_ctx *ctx, const int res[3], const double b_min[3], const double b_max[3],
+                                     const double *transform, const float calib[12], float z_num, float z_den,
+                                     int precision, int init_resolution, double threshold,
+                                     double *sdf_hr, double *sdf_lr, int64_t *n_evaluated, void *stream)
+{
+    if (!ctx) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (check_ready(ctx, precision)) return 1;
+    if (init_resolution < 1) SURS_FAIL(ctx, "surs_eval_grid_octree: bad init_resolution");
+    const size_t nnode = (size_t)res[0] * res[1] * res[2];
+    // lib/sdf.py:60-64: zeros, dirty = ones
+    SURS_CUDA(ctx, cudaMemsetAsync(sdf_hr, 0, nnode * sizeof(double), st));
+    SURS_CUDA(ctx, cudaMemsetAsync(sdf_lr, 0, nnode * sizeof(double), st));
+    if (n_evaluated) *n_evaluated = 0;
+    int reso = res[0] / init_resolution;                        // lib/sdf.py:66
+    if (reso <= 0) return 0;                                    // the reference returns zeros
+    if (surs_ensure(ctx, (void **)&ctx->dirty, &ctx->dirty_cap, nnode)) return 1;
+    SURS_CUDA(ctx, cudaMemsetAsync(ctx->dirty, 1, nnode, st));
+    PointIO io;
+    memset(&io, 0, sizeof(io));
+    if (setup_grid(ctx, io, res, b_min, b_max, transform, st)) return 1;
+    fill_proj(io, calib, z_num, z_den);
+    io.vol_hr = sdf_hr;
+    io.vol_lr = sdf_lr;
+    while (reso > 0) {
+        const size_t cand = (size_t)((res[0] + reso - 1) / reso) * ((res[1] + reso - 1) / reso) * ((res[2] + reso - 1) / reso);
+        if (surs_ensure(ctx, (void **)&ctx->idx_list, &ctx->idx_cap, cand * sizeof(int64_t))) return 1;
+        int64_t nsel = 0;
+        if (surs_octree_select_impl(ctx, res, reso, ctx->dirty, ctx->idx_list, &nsel, st)) return 1;
+        if (n_evaluated) *n_evaluated += nsel;
+        const int64_t chunk = (int64_t)1 << 30;
+        for (int64_t s = 0; s < nsel; s += chunk) {
+            PointIO part = io;
+            part.idx_list = ctx->idx_list + s;
+            part.n = (nsel - s < chunk) ? nsel - s : chunk;
+            if (run_query(ctx, part, precision, st)) return 1;
+        }
+        if (reso <= 1) break;                                   // lib/sdf.py:79
+        if (surs_octree_cells_impl(ctx, res, reso, threshold, sdf_hr, sdf_lr, ctx->dirty, st)) return 1;
+        reso /= 2;
+    }
+    return 0;
+}
+
+__global__ void cast_kernel(const double *__restrict__ src, float *__restrict__ dst, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = (float)src[i];
+}
+
+extern "C" int surs_cast_f64_f32(surs_ctx *ctx, const double *src, float *dst, int64_t n, void *stream)
+{
+    if (!ctx) return 1;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n <= 0) return 0;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > ctx->sm_count * 32) blocks = ctx->sm_count * 32;
+    cast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    SURS_LAUNCH_CHECK(ctx, "cast_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// OBJ writer (host): lib/mesh_util.py:53-61
+// ------------------------------------------------------------------------------------
+extern "C" int surs_save_obj_mesh(const char *path, const double *verts, int64_t n_verts,
+                                  const int32_t *faces, int64_t n_faces)
+{
+    FILE *f = fopen(path, "w");
+    if (!f) return 1;
+    static const size_t BUF = 1 << 20;
+    char *buf = (char *)malloc(BUF + 256);
+    if (!buf) { fclose(f); return 1; }
+    size_t used = 0;
+    for (int64_t i = 0; i < n_verts; ++i) {
+        used += (size_t)snprintf(buf + used, 256, "v %.4f %.4f %.4f\n", verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]);
+        if (used >= BUF) { fwrite(buf, 1, used, f); used = 0; }
+    }
+    for (int64_t i = 0; i < n_faces; ++i) {
+        used += (size_t)snprintf(buf + used, 256, "f %d %d %d\n", faces[3 * i] + 1, faces[3 * i + 2] + 1, faces[3 * i + 1] + 1);
+        if (used >= BUF) { fwrite(buf, 1, used, f); used = 0; }
+    }
+    if (used) fwrite(buf, 1, used, f);
+    free(buf);
+    return fclose(f) != 0;
+}

@@ -1,0 +1,238 @@
+"""GPU parity tests: every CUDA path is driven through the C-ABI (surs_b200._capi.Context) and
+compared with the CPU oracle / golden fixtures.  Run on the B200 box: pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import mc_oracle
+from oracle import surs_oracle as O
+from surs_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+# tolerances, pre-threshold occupancy.  FP32 mode is an fp32 FMA chain (reference is fp32 too).
+TOL_FP32 = 2e-5
+# FP16 mode: fp16 operands (11-bit significand), fp32 accumulate.  Stated tolerance: max |d| <= 5e-3
+# and mean |d| <= 3e-4 on the synthetic saturating weights (measured values are printed).
+TOL_FP16_MAX = 5e-3
+TOL_FP16_MEAN = 3e-4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from surs_b200 import _capi
+    c = _capi.Context("cuda:0")
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def case32(ctx):
+    case = syn.SyntheticCase(S=32, seed=0)
+    load_case(ctx, case)
+    return case
+
+
+def load_case(ctx, case):
+    dev = ctx.device
+    t = lambda a: torch.from_numpy(a).to(dev)
+    ctx.set_weights([t(w) for w in case.mlp_lr[0]], [t(b) for b in case.mlp_lr[1]],
+                    [t(w) for w in case.mlp_hr[0]], [t(b) for b in case.mlp_hr[1]],
+                    syn.MLP_DIM_LR, syn.MLP_DIM_HR, syn.RES_LAYERS)
+    ctx.set_features(t(case.feat_lr), t(case.feat_hr))
+
+
+def znum(case):
+    return float(case.load_size // 2), float(case.z_size)
+
+
+def test_umma_selftest(ctx):
+    """The tcgen05 plumbing in isolation: descriptors, swizzled K-major layout, TMEM read-back."""
+    g = torch.Generator().manual_seed(0)
+    for (N, K, tail) in ((256, 64, False), (256, 128, False), (144, 128, False), (256, 80, True), (144, 192, False), (64, 16, True)):
+        A = torch.randn(128, K, generator=g)
+        B = torch.randn(N, K, generator=g)
+        D = ctx.selftest_umma(A, B, tail16=tail).cpu()
+        ref = A.half().float() @ B.half().float().T
+        err = (D - ref).abs().max().item()
+        assert err < 2e-3, (N, K, tail, err)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_query_matches_golden_and_oracle(ctx, case32, golden_dir, prec):
+    from surs_b200 import _capi
+    g = np.load(os.path.join(golden_dir, "query_golden.npz"))
+    pts = torch.from_numpy(g["points"]).to(ctx.device)
+    p = _capi.PREC_FP32 if prec == "fp32" else _capi.PREC_FP16
+    for calib, khr, klr in ((case32.calib, "pred_hr", "pred_lr"), (g["calib2"], "pred_hr2", "pred_lr2")):
+        hr, lr = ctx.query(pts, calib, *znum(case32), precision=p)
+        hr, lr = hr.cpu().numpy(), lr.cpu().numpy()
+        dh, dl = np.abs(hr - g[khr]), np.abs(lr - g[klr])
+        print("query %s: max|d| hr %.3g lr %.3g  mean hr %.3g lr %.3g" % (prec, dh.max(), dl.max(), dh.mean(), dl.mean()))
+        if prec == "fp32":
+            assert dh.max() < TOL_FP32 and dl.max() < TOL_FP32
+        else:
+            assert dh.max() < TOL_FP16_MAX and dl.max() < TOL_FP16_MAX
+            assert dh.mean() < TOL_FP16_MEAN and dl.mean() < TOL_FP16_MEAN
+        # out-of-image points are exactly 0 (mask multiply), bit exact in both modes
+        assert np.array_equal(hr == 0, g[khr] == 0) and np.array_equal(lr == 0, g[klr] == 0)
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 5000, 40000])
+def test_query_ragged_sizes_fp16_vs_fp32(ctx, case32, n):
+    from surs_b200 import _capi
+    pts = torch.from_numpy(syn.random_points(n, seed=n)).to(ctx.device)
+    a = ctx.query(pts, case32.calib, *znum(case32), precision=_capi.PREC_FP32)
+    b = ctx.query(pts, case32.calib, *znum(case32), precision=_capi.PREC_FP16)
+    for x, y in zip(a, b):
+        d = (x - y).abs()
+        assert d.max().item() < TOL_FP16_MAX, d.max().item()
+    # classification at 0.5 must agree except for near-threshold points (reported)
+    flips = ((a[0] > 0.5) != (b[0] > 0.5))
+    near = (a[0] - 0.5).abs() < TOL_FP16_MAX
+    assert not (flips & ~near).any()
+
+
+def test_query_empty_and_host_path(ctx, case32):
+    from surs_b200 import _capi
+    hr, lr = ctx.query(torch.empty(3, 0, device=ctx.device), case32.calib, *znum(case32))
+    assert hr.numel() == 0 and lr.numel() == 0
+    pts = syn.random_points(3000, seed=9)
+    h1, l1 = ctx.query_host(pts, case32.calib, *znum(case32), precision=_capi.PREC_FP32)
+    h2, l2 = ctx.query(torch.from_numpy(pts).to(ctx.device), case32.calib, *znum(case32), precision=_capi.PREC_FP32)
+    assert np.array_equal(h1, h2.cpu().numpy()) and np.array_equal(l1, l2.cpu().numpy())
+
+
+def test_dense_grid_matches_reference_volumes(ctx, case32, golden_dir):
+    from surs_b200 import _capi
+    g = np.load(os.path.join(golden_dir, "recon_golden.npz"))
+    for prec, tol in ((_capi.PREC_FP32, TOL_FP32), (_capi.PREC_FP16, TOL_FP16_MAX)):
+        hr, lr = ctx.eval_grid((32, 32, 32), [-0.5] * 3, [0.5] * 3, case32.calib, *znum(case32), precision=prec)
+        assert np.abs(hr.cpu().numpy() - g["dense32_hr"]).max() < tol
+        assert np.abs(lr.cpu().numpy() - g["dense32_lr"]).max() < tol
+    # slab evaluation = the corresponding planes of the full grid, bit exact
+    full = ctx.eval_grid((32, 32, 32), [-0.5] * 3, [0.5] * 3, case32.calib, *znum(case32), precision=_capi.PREC_FP16)
+    slab = ctx.eval_grid((32, 32, 32), [-0.5] * 3, [0.5] * 3, case32.calib, *znum(case32), precision=_capi.PREC_FP16,
+                         plane_lo=7, plane_hi=20)
+    assert torch.equal(full[0][7:20], slab[0]) and torch.equal(full[1][7:20], slab[1])
+    # with a transform the grid equals explicit points from the oracle's create_grid
+    T = np.array([[0.9, 0.1, 0.0, 0.01], [-0.1, 0.9, 0.05, -0.02], [0.0, -0.05, 1.1, 0.03], [0, 0, 0, 1.0]])
+    coords, _ = O.create_grid(16, 12, 20, np.array([-0.5] * 3), np.array([0.5, 0.4, 0.5]), transform=T)
+    pts = torch.from_numpy(coords.reshape(3, -1).astype(np.float32)).to(ctx.device)
+    a = ctx.query(pts, case32.calib, *znum(case32), precision=_capi.PREC_FP32)
+    b = ctx.eval_grid((16, 12, 20), [-0.5] * 3, [0.5, 0.4, 0.5], case32.calib, *znum(case32), transform=T, precision=_capi.PREC_FP32)
+    assert torch.equal(a[0], b[0].reshape(-1)) and torch.equal(a[1], b[1].reshape(-1))
+
+
+def test_octree_blocks_match_reference_golden(ctx, golden_dir):
+    """select / cells kernels driven by the analytic eval_func: bit exact vs lib/sdf.py's output."""
+    g = np.load(os.path.join(golden_dir, "octree_golden.npz"))
+    coords, _ = O.create_grid(64, 64, 64, np.array([-0.5] * 3), np.array([0.5] * 3))
+    flat = coords.reshape(3, -1)
+    for thr, init, kh, kl in ((0.05, 16, "oct64_hr", "oct64_lr"), (0.11, 8, "oct64b_hr", "oct64b_lr")):
+        res = (64, 64, 64)
+        hr = torch.zeros(res, device=ctx.device, dtype=torch.float64)
+        lr = torch.zeros(res, device=ctx.device, dtype=torch.float64)
+        dirty = torch.ones(res, device=ctx.device, dtype=torch.uint8)
+        idx = torch.empty(64 ** 3, device=ctx.device, dtype=torch.int64)
+        reso = 64 // init
+        while reso > 0:
+            n = ctx.octree_select(res, reso, dirty, idx)
+            sel = idx[:n].cpu().numpy()
+            a, b = helpers.analytic_eval_func(flat[:, sel])
+            hr.view(-1)[idx[:n]] = torch.from_numpy(a.reshape(-1).astype(np.float64)).to(ctx.device)
+            lr.view(-1)[idx[:n]] = torch.from_numpy(b.reshape(-1).astype(np.float64)).to(ctx.device)
+            if reso <= 1:
+                break
+            ctx.octree_cells(res, reso, thr, hr, lr, dirty)
+            reso //= 2
+        assert np.array_equal(hr.cpu().numpy(), g[kh]), kh
+        assert np.array_equal(lr.cpu().numpy(), g[kl]), kl
+
+
+def test_fused_octree_equals_oracle_octree_on_same_occupancies(ctx, case32):
+    from surs_b200 import _capi
+    for prec in (_capi.PREC_FP32, _capi.PREC_FP16):
+        res = (64, 64, 64)
+        hr, lr, n_eval = ctx.eval_grid_octree(res, [-0.5] * 3, [0.5] * 3, case32.calib, *znum(case32), threshold=0.05,
+                                              init_resolution=16, precision=prec)
+
+        def eval_func(points):
+            p = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float32)).to(ctx.device)
+            a, b = ctx.query(p, case32.calib, *znum(case32), precision=prec)
+            return a.cpu().numpy(), b.cpu().numpy()
+
+        stats = []
+        coords, _ = O.create_grid(*res, np.array([-0.5] * 3), np.array([0.5] * 3))
+        ohr, olr = O.eval_grid_octree(0.05, coords, eval_func, init_resolution=16, num_samples=50000, stats=stats)
+        assert np.array_equal(hr.cpu().numpy(), ohr) and np.array_equal(lr.cpu().numpy(), olr)
+        assert n_eval == sum(s[1] for s in stats)
+        assert n_eval < 64 ** 3       # something was pruned
+    # R < init_resolution: zeros, as the reference
+    z = ctx.eval_grid_octree((32, 32, 32), [-0.5] * 3, [0.5] * 3, case32.calib, *znum(case32), threshold=0.05, init_resolution=64)
+    assert not z[0].any() and not z[1].any() and z[2] == 0
+
+
+def _mc_check(ctx, vol, level=0.5, mat=None):
+    v, f, n, val, st = mc_oracle.marching_cubes_lewiner(vol, level, return_stats=True)
+    gv, gw, gf, gn, gval, gamb = ctx.marching_cubes(torch.from_numpy(vol).to(ctx.device), level, mat)
+    assert gf.shape[0] == f.shape[0] and gv.shape[0] == v.shape[0]
+    assert np.array_equal(gf.cpu().numpy(), f)                      # topology bit exact
+    assert np.abs(gv.cpu().numpy() - v).max() <= 1e-5               # positions (bit exact in practice)
+    assert np.array_equal(gv.cpu().numpy(), v)
+    assert np.abs(gn.cpu().numpy() - n).max() < 1e-4
+    assert np.array_equal(gval.cpu().numpy(), val)
+    assert gamb == st["ambiguous_cells"]
+    if mat is not None:
+        assert np.allclose(gw.cpu().numpy(), O.verts_to_world(mat, v), rtol=0, atol=1e-12)
+    return v, f
+
+
+def test_marching_cubes_matches_cpu_twin(ctx):
+    vol = helpers.sphere_volume(48, 15.3)
+    _, mat = O.create_grid(48, 48, 48, np.array([-0.5] * 3), np.array([0.5] * 3))
+    v, f = _mc_check(ctx, vol, mat=mat)
+    assert helpers.mesh_euler_closed(v, f) == 2
+    rng = np.random.default_rng(0)
+    noisy = rng.random((24, 20, 28)).astype(np.float32)             # many ambiguous cells, ragged shape
+    noisy[0] = noisy[-1] = 0; noisy[:, 0] = noisy[:, -1] = 0; noisy[:, :, 0] = noisy[:, :, -1] = 0
+    v, f = _mc_check(ctx, noisy)
+    helpers.mesh_euler_closed(v, f)
+    g = np.stack(np.meshgrid(*[np.arange(40)] * 3, indexing="ij")).astype(np.float64)
+    wavy = (np.sin(g[0] * 0.7) + np.sin(g[1] * 0.9) + np.sin(g[2] * 0.8)).astype(np.float32)   # open surface at the border
+    _mc_check(ctx, wavy, level=0.1)
+    _mc_check(ctx, np.ascontiguousarray(vol[:2]))                    # minimal thickness
+
+
+def test_marching_cubes_slabs_reproduce_single_volume(ctx):
+    """Three slabs with the seam protocol (SURS_MC_LOWER_FOREIGN + seam maps) == one volume."""
+    from surs_b200 import _capi
+    rng = np.random.default_rng(1)
+    vol = helpers.sphere_volume(40, 13.1) + 0.2 * rng.random((40, 40, 40)).astype(np.float32)
+    v, f, _, _ = mc_oracle.marching_cubes_lewiner(vol, 0.5)
+    cuts = [0, 13, 27, 40]
+    dev = ctx.device
+    verts, faces, offset, seam = [], [], 0, None
+    for r in range(3):
+        lo, hi = cuts[r], min(cuts[r + 1] + 1, 40)                  # + 1 halo plane
+        slab = torch.from_numpy(np.ascontiguousarray(vol[lo:hi])).to(dev)
+        nv, nf, _ = ctx.mc_count(slab, 0.5, flags=_capi.MC_LOWER_FOREIGN if r > 0 else 0)
+        seam_out = torch.empty((2, 40, 40), device=dev, dtype=torch.int32)
+        vv, _, _, _ = ctx.mc_emit_verts(nv, None, vert_id_offset=offset, seam_out=seam_out)
+        ff = ctx.mc_emit_faces(nf, seam_in=seam)
+        vv = vv.clone()
+        vv[:, 0] += cuts[r]
+        verts.append(vv.cpu().numpy())
+        faces.append(ff.cpu().numpy())
+        offset += nv
+        seam = seam_out
+    assert np.array_equal(np.concatenate(verts), v)
+    assert np.array_equal(np.concatenate(faces), f)
+
+
+def test_marching_cubes_no_surface_gives_zero_counts(ctx):
+    vol = torch.zeros((8, 8, 8), device=ctx.device)
+    assert ctx.mc_count(vol, 0.5)[:2] == (0, 0)
