@@ -138,7 +138,9 @@ int surs_octree_cells(surs_ctx *ctx, const int res[3], int reso, double threshol
  * faces reference them through seam_in [dev] int32 [2,res1,res2] (global ids; axis-1 edges
  * then axis-2 edges), which is the lower slab's seam_out [dev] int32 [2,res1,res2] (ids of
  * the vertices lying in its LAST plane, -1 where there is none).  vert_id_offset (the sum of
- * the vertex counts of all lower slabs) is added to every id written to faces / seam_out.
+ * the vertex counts of all lower slabs) is added to every id written to faces / seam_out;
+ * plane_offset (the slab's first plane in the full grid) is added to the axis-0 coordinate
+ * before interpolation, so positions are bit identical to the single-volume result.
  * So: count everywhere -> exchange counts -> emit_verts everywhere -> pass seam_out up ->
  * emit_faces everywhere -> concatenate in rank order.
  * n_ambiguous [host, may be NULL]: number of cells with an ambiguous face (the part of the
@@ -149,7 +151,8 @@ int surs_mc_count(surs_ctx *ctx, const float *vol, const int res[3], float level
 int surs_mc_emit(surs_ctx *ctx, const double *mat, float *verts, double *verts_world,
                  int32_t *faces, float *normals, float *values, void *stream);
 int surs_mc_emit_verts(surs_ctx *ctx, const double *mat, float *verts, double *verts_world,
-                       float *normals, float *values, int64_t vert_id_offset, int32_t *seam_out, void *stream);
+                       float *normals, float *values, int64_t vert_id_offset, int plane_offset,
+                       int32_t *seam_out, void *stream);
 int surs_mc_emit_faces(surs_ctx *ctx, int32_t *faces, const int32_t *seam_in, void *stream);
 
 /* float64 -> float32 cast of a volume (what skimage does to its input); n elements. */

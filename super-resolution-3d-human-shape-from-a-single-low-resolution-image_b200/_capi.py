@@ -44,7 +44,7 @@ SIGNATURES = {
     "surs_octree_cells": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_double, _P, _P, _P, _P]),
     "surs_mc_count": (ctypes.c_int, [_P, _P, _P, ctypes.c_float, ctypes.c_int, _P, _P, _P, _P]),
     "surs_mc_emit": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
-    "surs_mc_emit_verts": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _P]),
+    "surs_mc_emit_verts": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, ctypes.c_int, _P, _P]),
     "surs_mc_emit_faces": (ctypes.c_int, [_P, _P, _P, _P]),
     "surs_cast_f64_f32": (ctypes.c_int, [_P, _P, _P, _I64, _P]),
     "surs_save_obj_mesh": (ctypes.c_int, [ctypes.c_char_p, _P, _I64, _P, _I64]),
@@ -261,7 +261,7 @@ class Context:
         self._mc_vol = vol            # borrowed until the emit calls ran
         return int(nv.value), int(nf.value), int(na.value)
 
-    def mc_emit_verts(self, n_verts, mat=None, vert_id_offset=0, seam_out=None, want_normals=True):
+    def mc_emit_verts(self, n_verts, mat=None, vert_id_offset=0, seam_out=None, want_normals=True, plane_offset=0):
         verts = torch.empty((n_verts, 3), device=self.device, dtype=torch.float32)
         normals = torch.empty((n_verts, 3), device=self.device, dtype=torch.float32) if want_normals else None
         values = torch.empty((n_verts,), device=self.device, dtype=torch.float32) if want_normals else None
@@ -269,7 +269,7 @@ class Context:
         m = None if mat is None else np.ascontiguousarray(np.asarray(mat, dtype=np.float64)[:3, :4])
         with torch.cuda.device(self.device):
             self._check(self.lib.surs_mc_emit_verts(self._h, None if m is None else m.ctypes.data, _ptr(verts), _ptr(world),
-                                                    _ptr(normals), _ptr(values), int(vert_id_offset), _ptr(seam_out),
+                                                    _ptr(normals), _ptr(values), int(vert_id_offset), int(plane_offset), _ptr(seam_out),
                                                     _stream(self.device)))
         return verts, world, normals, values
 

@@ -209,6 +209,7 @@ struct McOut {
     int has_mat;
     int32_t *vid;          // [nnode][3] edge -> global vertex id
     int64_t id_offset;
+    int plane_offset;      // index of the volume's plane 0 along axis 0 in the full grid (slabs)
 };
 
 __device__ __forceinline__ void write_vertex(const McOut &o, int64_t v, const double pos[3], const double g[3], double value)
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_verts_kernel(McParams p, i
         const int ei = bi + (axis == 0), ej = bj + (axis == 1), ek = bk + (axis == 2);
         const int ca = c_edge_corner[2 * e], cb = c_edge_corner[2 * e + 1];
         const int lo = c_corner_off[3 * ca + axis] == 0 ? ca : cb, hi = lo == ca ? cb : ca;
-        double pos[3] = {(double)bi, (double)bj, (double)bk};
+        double pos[3] = {(double)(bi + o.plane_offset), (double)bj, (double)bk};
         const double base = pos[axis];
         const double x = edge_point(base, c.d[lo], c.d[hi]);
         pos[axis] = x;
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_verts_kernel(McParams p, i
             if ((c.d[ca] > 0.0) == (c.d[cb] > 0.0)) continue;
             const int axis = c_edge_axis[e];
             const int lo = c_corner_off[3 * ca + axis] == 0 ? ca : cb, hi = lo == ca ? cb : ca;
-            double q[3] = {(double)(i + c_edge_base[3 * e]), (double)(j + c_edge_base[3 * e + 1]), (double)(k + c_edge_base[3 * e + 2])};
+            double q[3] = {(double)(i + o.plane_offset + c_edge_base[3 * e]), (double)(j + c_edge_base[3 * e + 1]), (double)(k + c_edge_base[3 * e + 2])};
             q[axis] = edge_point(q[axis], c.d[lo], c.d[hi]);
             s[0] = __dadd_rn(s[0], q[0]); s[1] = __dadd_rn(s[1], q[1]); s[2] = __dadd_rn(s[2], q[2]);
             ++n;
@@ -448,7 +449,8 @@ extern "C" int surs_mc_count(surs_ctx *ctx, const float *vol, const int res[3], 
 }
 
 extern "C" int surs_mc_emit_verts(surs_ctx *ctx, const double *mat, float *verts, double *verts_world,
-                                  float *normals, float *values, int64_t vert_id_offset, int32_t *seam_out, void *stream)
+                                  float *normals, float *values, int64_t vert_id_offset, int plane_offset,
+                                  int32_t *seam_out, void *stream)
 {
     if (!ctx) return 1;
     cudaStream_t st = (cudaStream_t)stream;
@@ -466,6 +468,7 @@ extern "C" int surs_mc_emit_verts(surs_ctx *ctx, const double *mat, float *verts
     if (mat) memcpy(o.mat, mat, sizeof(double) * 12);
     o.vid = ctx->mc_vid;
     o.id_offset = vert_id_offset;
+    o.plane_offset = plane_offset;
     ctx->mc_id_offset = vert_id_offset;
     if (ctx->mc_nv > 0) {
         mc_emit_verts_kernel<<<(unsigned)nblocks, MC_THREADS, 0, st>>>(p, nnode, ctx->mc_block_tot, o);
@@ -501,6 +504,6 @@ extern "C" int surs_mc_emit_faces(surs_ctx *ctx, int32_t *faces, const int32_t *
 extern "C" int surs_mc_emit(surs_ctx *ctx, const double *mat, float *verts, double *verts_world,
                             int32_t *faces, float *normals, float *values, void *stream)
 {
-    if (surs_mc_emit_verts(ctx, mat, verts, verts_world, normals, values, 0, nullptr, stream)) return 1;
+    if (surs_mc_emit_verts(ctx, mat, verts, verts_world, normals, values, 0, 0, nullptr, stream)) return 1;
     return surs_mc_emit_faces(ctx, faces, nullptr, stream);
 }

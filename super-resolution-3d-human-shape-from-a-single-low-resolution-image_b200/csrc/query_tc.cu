@@ -259,11 +259,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_tc_kernel(PointIO io, TcPar
                     if (h == 0) {
                         epilogue_256(lane_t1, prm.bias[m][1], row, lane, 0u, scratch, bars, 0u);
                         ptx::fence_proxy_async_all();
-                        __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&bars->scr_ready);
                     } else {
                         epilogue_256(lane_t1, prm.bias[m][1] + 256, row, lane, a_smem, nullptr, bars, afill & 1u);
                         ++afill;
+                        // Only now may the reload warp start waiting on a_free: mbarrier parity waits
+                        // are only meaningful one phase ahead, and its fill is the next one.
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&bars->scr_ready);
                     }
                     ptx::tc_fence_before();
                     __syncwarp();

@@ -1,0 +1,224 @@
+"""Drop-in for the reference's ``lib/model/SuRSNet.py`` (+ ``BaseSuRSNet.py``) on the query side.
+
+Same public surface: ``super_res``, ``filter_lr``, ``filter_hr``, ``query_mr``, ``query_sr``,
+``get_preds``, attributes ``num_views``, ``preds_hr``, ``preds_lr``, ``im_feat_list_lr``,
+``im_feat_list_hr`` -- plus the PIFu aliases ``filter(images)`` and ``query(points, calibs, ...)``
+that are empty stubs in the reference (lib/model/BaseSuRSNet.py:50-56,66-78).
+
+The two SurfaceClassifier MLPs keep the reference's state-dict keys
+(``mlp_{lr,hr}.conv{0..4}.{weight,bias}``), so a reference checkpoint's MLP part loads unchanged.
+The image encoder (SuRSSR_v3 + HGFilter, kept in PyTorch by design) is pluggable: pass
+``encoder=`` (any module with ``super_res`` / ``filter_lr`` / ``filter_hr`` semantics) or use
+``lib.model.encoder.build_encoder(opt)``.
+
+Query semantics (reference lib/model/SuRSNet.py:131-187): ``query_mr`` computes the LR
+prediction, ``query_sr`` appends the MASKED LR prediction as channel 321 and computes the HR one;
+the fused kernel produces both in one launch, so ``query_mr`` runs it and ``query_sr`` on the
+same points returns the cached HR result.  The stray ``print("z", z)`` of
+lib/model/DepthNormalizer.py:17 is intentionally not reproduced.
+
+Not covered by the kernels -> explicit torch path (a warning is issued once, never silent):
+``num_views > 1``, image-space ``transforms``, perspective projection, ``--no_residual``,
+non-default ``mlp_dim`` / ``mlp_res_layers``, training mode (3 hourglass outputs).
+"""
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import geometry
+from ... import _capi
+from .SurfaceClassifier import SurfaceClassifier
+
+_DEFAULT_LR = [321, 1024, 512, 256, 128, 1]
+_DEFAULT_HR = [322, 1024, 512, 256, 128, 1]
+
+
+def _fingerprint(tensors):
+    return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+
+
+class SuRSNet(nn.Module):
+    def __init__(self, opt, projection_mode="orthogonal", error_term=None, encoder=None, precision=_capi.PREC_FP16):
+        super().__init__()
+        self.name = "surs_b200"
+        self.opt = opt
+        self.num_views = opt.num_views
+        self.projection_mode = projection_mode
+        self.projection = geometry.orthogonal if projection_mode == "orthogonal" else geometry.perspective
+        self.index = geometry.index
+        self.error_term = error_term if error_term is not None else nn.MSELoss()
+        self.precision = precision
+        self.mlp_lr = SurfaceClassifier(opt.mlp_dim_lr, opt.num_views, opt.no_residual, opt.mlp_res_layers_lr, nn.Sigmoid())
+        self.mlp_hr = SurfaceClassifier(opt.mlp_dim_hr, opt.num_views, opt.no_residual, opt.mlp_res_layers_hr, nn.Sigmoid())
+        self.encoder = encoder
+        self.im_feat_list_lr = []
+        self.im_feat_list_hr = []
+        self.intermediate_preds_list_lr = []
+        self.intermediate_preds_list_hr = []
+        self.im_SR = self.feature_lr = self.feature_hr = None
+        self.preds_lr = self.preds_hr = None
+        self.labels_lr = self.labels_hr = None
+        self._ctx = None
+        self._w_fp = self._f_fp = self._q_fp = None
+        self._cached_hr = None
+        self._warned = set()
+
+    # ------------------------------------------------------------------ encoder side (PyTorch)
+    def _need_encoder(self):
+        if self.encoder is None:
+            raise RuntimeError("this SuRSNet was built without an image encoder; pass encoder= or set "
+                               "im_feat_list_lr / im_feat_list_hr yourself")
+        return self.encoder
+
+    def super_res(self, images):
+        """reference lib/model/SuRSNet.py:124-129."""
+        self.im_SR, self.feature_lr, self.feature_hr = self._need_encoder().super_res(images)
+        return self.im_SR, self.feature_lr, self.feature_hr
+
+    def filter_lr(self, images):
+        """reference lib/model/SuRSNet.py:101-110: keeps only the last hourglass output in eval mode."""
+        self.im_feat_list_lr = self._need_encoder().filter_lr(images)
+        if not self.training:
+            self.im_feat_list_lr = [self.im_feat_list_lr[-1]]
+
+    def filter_hr(self, images):
+        """reference lib/model/SuRSNet.py:112-122."""
+        self.im_feat_list_hr = self._need_encoder().filter_hr(images)
+        if not self.training:
+            self.im_feat_list_hr = [self.im_feat_list_hr[-1]]
+
+    def filter(self, images):
+        """PIFu-style alias: the whole encoder (what gen_mesh does, lib/train_util.py:57-59)."""
+        _, feature_lr, feature_hr = self.super_res(images)
+        self.filter_hr(feature_hr)
+        self.filter_lr(feature_lr)
+
+    # ------------------------------------------------------------------ accelerated context
+    def surs_context(self):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("surs_b200 runs on a B200; move the network to a CUDA device (there is no CPU path)")
+        if self._ctx is None or self._ctx.device != dev:
+            self._ctx = _capi.Context(dev)
+            self._w_fp = self._f_fp = None
+        return self._ctx
+
+    def depth_scale(self):
+        """reference lib/model/DepthNormalizer.py:18: z * (loadSize // 2) / z_size."""
+        return float(self.opt.loadSize // 2), float(self.opt.z_size)
+
+    def _kernel_config_ok(self):
+        return (self.num_views == 1 and self.projection_mode == "orthogonal" and not self.opt.no_residual
+                and list(self.opt.mlp_dim_lr) == _DEFAULT_LR and list(self.opt.mlp_dim_hr) == _DEFAULT_HR
+                and list(self.opt.mlp_res_layers_lr) == [2, 3, 4] and list(self.opt.mlp_res_layers_hr) == [2, 3, 4]
+                and not self.training)
+
+    def can_accelerate(self, calibs=None, transforms=None):
+        ok = self._kernel_config_ok() and transforms is None
+        if ok and calibs is not None and torch.is_tensor(calibs) and calibs.dim() == 3 and calibs.shape[0] != 1:
+            ok = False
+        if ok:
+            self._sync()
+        return ok
+
+    def _sync(self):
+        """Pushes MLP parameters / feature maps to the library when they changed."""
+        ctx = self.surs_context()
+        params = [c.weight for c in self.mlp_lr.layers()] + [c.bias for c in self.mlp_lr.layers()] + \
+                 [c.weight for c in self.mlp_hr.layers()] + [c.bias for c in self.mlp_hr.layers()]
+        fp = _fingerprint(params)
+        if fp != self._w_fp:
+            ctx.set_weights([c.weight for c in self.mlp_lr.layers()], [c.bias for c in self.mlp_lr.layers()],
+                            [c.weight for c in self.mlp_hr.layers()], [c.bias for c in self.mlp_hr.layers()],
+                            self.opt.mlp_dim_lr, self.opt.mlp_dim_hr, self.opt.mlp_res_layers_lr)
+            self._w_fp = fp
+            self._q_fp = None
+        if not self.im_feat_list_lr or not self.im_feat_list_hr:
+            raise RuntimeError("image features missing: call filter_lr / filter_hr (or filter) before querying")
+        feats = [self.im_feat_list_lr[-1], self.im_feat_list_hr[0]]
+        fp = _fingerprint(feats)
+        if fp != self._f_fp:
+            ctx.set_features(feats[0], feats[1])
+            self._f_fp = fp
+            self._q_fp = None
+
+    def _warn_once(self, why):
+        if why not in self._warned:
+            self._warned.add(why)
+            warnings.warn("surs_b200: %s is not covered by the fused CUDA query; using the torch path" % why)
+
+    # ------------------------------------------------------------------ queries
+    def _fused(self, points, calibs):
+        ctx = self.surs_context()
+        pts = points[0] if points.dim() == 3 else points
+        zn, zd = self.depth_scale()
+        hr, lr = ctx.query(pts, calibs, zn, zd, precision=self.precision)
+        return hr.view(1, 1, -1), lr.view(1, 1, -1)
+
+    def query_mr(self, points, calibs, transforms=None, labels=None):
+        """reference lib/model/SuRSNet.py:131-159."""
+        if labels is not None:
+            self.labels_lr = labels
+        if not self.can_accelerate(calibs, transforms):
+            return self._query_mr_torch(points, calibs, transforms)
+        hr, lr = self._fused(points, calibs)
+        self.preds_lr = lr
+        self.intermediate_preds_list_lr = [lr]
+        self._cached_hr = hr
+        self._q_fp = _fingerprint([points, calibs])
+
+    def query_sr(self, points, calibs, transforms=None, labels=None):
+        """reference lib/model/SuRSNet.py:161-187 (requires query_mr on the same points first)."""
+        if labels is not None:
+            self.labels_hr = labels
+        if not self.can_accelerate(calibs, transforms):
+            return self._query_sr_torch(points, calibs, transforms)
+        if self._q_fp is not None and self._q_fp == _fingerprint([points, calibs]) and self._cached_hr is not None:
+            hr = self._cached_hr
+        else:
+            # different points than query_mr saw: the reference would mix them; we recompute both consistently
+            hr, _ = self._fused(points, calibs)
+        self.preds_hr = hr
+        self.intermediate_preds_list_hr = [hr]
+
+    def query(self, points, calibs, transforms=None, labels=None):
+        """PIFu-style alias: query_mr + query_sr; returns the HR prediction."""
+        self.query_mr(points, calibs, transforms, labels)
+        self.query_sr(points, calibs, transforms, labels)
+        return self.preds_hr
+
+    def get_preds(self):
+        """reference lib/model/BaseSuRSNet.py:80-85 -- HR first."""
+        return self.preds_hr, self.preds_lr
+
+    # ------------------------------------------------------------------ torch path (uncovered variants)
+    def _local_features(self, points, calibs, transforms):
+        xyz = self.projection(points, calibs, transforms)
+        xy, z = xyz[:, :2, :], xyz[:, 2:3, :]
+        in_img = (xy[:, 0] >= -1.0) & (xy[:, 0] <= 1.0) & (xy[:, 1] >= -1.0) & (xy[:, 1] <= 1.0)
+        zn, zd = self.depth_scale()
+        z_feat = z * zn / zd
+        feats = [torch.cat([self.index(f, xy), self.index(self.im_feat_list_hr[0], xy), z_feat], 1)
+                 for f in self.im_feat_list_lr]
+        return feats, in_img[:, None].float()
+
+    def _query_mr_torch(self, points, calibs, transforms):
+        self._warn_once("this configuration (multi-view / transforms / perspective / non-default MLP / training)")
+        feats, mask = self._local_features(points, calibs, transforms)
+        self.point_local_feat = feats
+        self.intermediate_preds_list_lr = [mask * self.mlp_lr(f) for f in feats]
+        self.preds_lr = self.intermediate_preds_list_lr[-1]
+
+    def _query_sr_torch(self, points, calibs, transforms):
+        feats, mask = self._local_features(points, calibs, transforms)
+        self.intermediate_preds_list_hr = [mask * self.mlp_hr(torch.cat([f, p], 1))
+                                           for f, p in zip(feats, self.intermediate_preds_list_lr)]
+        self.preds_hr = self.intermediate_preds_list_hr[-1]
+
+    def forward(self, points, images_lr, calibs, transforms=None):
+        self.filter(images_lr)
+        self.query_mr(points, calibs, transforms)
+        self.query_sr(points, calibs, transforms)
+        return self.get_preds()

@@ -100,3 +100,14 @@ def test_obj_text_matches_reference(golden_dir):
     with open(os.path.join(golden_dir, "obj_golden.txt")) as f:
         want = f.read()
     assert O.obj_text(inp["verts"], inp["faces"]) == want
+
+
+def test_torch_port_matches_reference(golden_dir, case32):
+    """The CPU-baseline port (oracle/torch_port.py) reproduces the reference's outputs."""
+    from oracle import torch_port
+    g = np.load(os.path.join(golden_dir, "query_golden.npz"))
+    port = torch_port.TorchPort(case32)
+    hr, lr = port.query(g["points"])
+    assert np.abs(hr - g["pred_hr"]).max() < 1e-5 and np.abs(lr - g["pred_lr"]).max() < 1e-5
+    hr2, lr2 = port.query(g["points"], g["calib2"])
+    assert np.abs(hr2 - g["pred_hr2"]).max() < 1e-5 and np.abs(lr2 - g["pred_lr2"]).max() < 1e-5
