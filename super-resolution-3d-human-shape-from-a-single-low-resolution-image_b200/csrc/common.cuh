@@ -132,6 +132,7 @@ struct surs_ctx {
     size_t tc_weights_bytes;
     void *tc_scratch;                      // 64 KB per CTA: first half of layer 1 between passes
     size_t tc_scratch_cap;
+    float tc_w4y[2][128];                  // W4[0, 0:128] of both MLPs (host copy, passed as kernel parameter)
     // ---- features, channels-last ------------------------------------------------
     int have_features;
     int H_lr, W_lr, H_hr, W_hr;

@@ -40,16 +40,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag)
+// `prof` (optional): cycles spent waiting are added to prof[tag] (profiling builds only).
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag, unsigned long long *prof = nullptr)
 {
-    if (mbar_try_wait(bar, parity)) return;
+    // try_wait may suspend the warp inside the instruction, so profiling must start the clock first
     const long long t0 = clock64();
+    if (mbar_try_wait(bar, parity)) {
+        if (prof) atomicAdd(prof + tag, (unsigned long long)(clock64() - t0));
+        return;
+    }
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) {   // ~2 s
             printf("surs: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
             __trap();
         }
     }
+    if (prof) atomicAdd(prof + tag, (unsigned long long)(clock64() - t0));
 }
 
 // ---------------------------------------------------------------- proxies / fences

@@ -6,48 +6,54 @@
 // shared memory in the UMMA K-major SWIZZLE_128B layout; then both SurfaceClassifier MLPs
 // (SurfaceClassifier.py:45-81) run as a chain of tcgen05.mma (M=128, N=256, K=16; fp16 in,
 // fp32 accumulate in TMEM).  Activations never leave the SM: each accumulator is read back
-// with tcgen05.ld, gets bias + leaky_relu, is rounded to fp16 and written as the next layer's
-// A operand.  The skip concat [y ; f] (SurfaceClassifier.py:63-64) is a second accumulation
-// from the resident F tile, never a materialised concat.  The 128->1 layer and the sigmoid
-// run in the epilogue of layer 3, whose GEMM carries W4's skip part as a 129th output column.
+// with tcgen05.ld, gets leaky_relu, is rounded to fp16 and written as the next layer's A operand.
+// The skip concat [y ; f] (SurfaceClassifier.py:63-64) is a second accumulation from the
+// resident F tile, never a materialised concat.  Biases ride on the tensor core too: F carries
+// two constant-one columns and the weight stream holds each bias as an fp16 hi+lo pair against
+// them (the 225 KB of shared memory leave no L1 for bias loads).  The 128->1 layer and the
+// sigmoid run in the epilogue of layer 3, whose GEMM carries W4's skip part (+ b4) as a 129th
+// output column.
 //
 // TMEM holds 512 fp32 columns per lane = two 256-column accumulators.  Layer 1 is 512 wide, so
 // it is produced in two halves and layer 0 (1024 wide, in four 256 chunks) is recomputed for
 // each half; the first half's activations wait in an L2-resident scratch line (64 KB per CTA)
 // and come back by bulk TMA for layer 2.
 //
-// Warp roles: 0-3 gather + epilogues (warp w owns TMEM lanes 32w..32w+31), 4 = MMA issue
-// (one elected lane), 5 = weight stream (cp.async.bulk of pre-swizzled 32 KB blocks laid out in
-// HBM in consumption order, 2-stage ring), 6 = scratch reload.  All hand-offs are mbarriers.
+// Warp roles: 0-7 gather + epilogues (warp w owns TMEM lanes 32(w%4).. and column half w/4),
+// 8 = MMA issue (one elected lane), 9 = weight stream (cp.async.bulk of pre-swizzled 32 KB
+// blocks laid out in HBM in consumption order, 3-stage ring), 10 = scratch reload.
+// All hand-offs are mbarriers; waits are bounded (a protocol bug traps instead of hanging).
 #include "common.cuh"
 #include "ptx.cuh"
+
+#include <stdlib.h>
 
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int KBLK = 64;                       // K elements per swizzle-128B block
 constexpr int A_BLK_BYTES = TILE_M * 128;      // 16 KB: 128 rows x 64 fp16
 constexpr int W_BLK_BYTES = 256 * 128;         // 32 KB: 256 rows x 64 fp16
 constexpr int W3_ROWS = 144;                   // layer 3: 128 outputs + W4's skip row + padding to 16
 constexpr int W3_BLK_BYTES = W3_ROWS * 128;
-constexpr int NF_BLK = 6;                      // F tile: 4 (lr) + 1 (hr) + 1 tail (z, pred_lr)
-constexpr int NA_BLK = 4;
-constexpr int NSTAGE = 2;
-constexpr int BLOCKS_PER_MLP = 8 * 6 + 8 * 4 + 14 + 10;     // 104
-constexpr int N256_BLOCKS_PER_MLP = 8 * 6 + 8 * 4 + 14;     // 94
+constexpr int NF_BLK = 6;                      // F tile: 4 (lr) + 1 (hr) + 1 tail (z, pred_lr, ones)
+constexpr int NA_SLOT = 2;                     // ring of A-operand K blocks (activations)
+constexpr int NSTAGE = 3;                      // weight ring
+constexpr int N256_BLOCKS_PER_MLP = 8 * 6 + 8 * 4 + 2 + 14;            // 96 blocks of 256 rows
+constexpr int BLOCKS_PER_MLP = N256_BLOCKS_PER_MLP + 10;               // + 10 blocks of 144 rows
 constexpr size_t MLP_BYTES = (size_t)N256_BLOCKS_PER_MLP * W_BLK_BYTES + 10 * (size_t)W3_BLK_BYTES;
-constexpr int A_FILLS_PER_MLP = 11;            // 8 x E0, E1(h=1), reload, E2
-constexpr int NTHREADS = 7 * 32;
+constexpr int A_FILLS_PER_MLP = 11;            // 8 x E0, E1(h=1), reload, E2 (4 K blocks each)
+constexpr int NEPI = 8;                        // gather / epilogue warps
+constexpr int NTHREADS = (NEPI + 3) * 32;
 
 constexpr int SMEM_F = 0;
 constexpr int SMEM_A = SMEM_F + NF_BLK * A_BLK_BYTES;
-constexpr int SMEM_W = SMEM_A + NA_BLK * A_BLK_BYTES;
+constexpr int SMEM_W = SMEM_A + NA_SLOT * A_BLK_BYTES;
 constexpr int SMEM_BAR = SMEM_W + NSTAGE * W_BLK_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;          // + barriers + alignment slack
 
 struct Bars {
     uint64_t full_w[NSTAGE], empty_w[NSTAGE];
-    uint64_t a_ready[NA_BLK], a_free[NA_BLK];
+    uint64_t a_ready[NA_SLOT], a_free[NA_SLOT];
     uint64_t acc_full[2], acc_free[2];
     uint64_t f_ready, scr_ready;
     uint32_t tmem_base;
@@ -55,16 +61,15 @@ struct Bars {
 
 struct TcParams {
     const uint8_t *weights;                    // 2 x MLP_BYTES
-    const float *bias[2][SURS_NUM_LAYERS];
-    const float *w4y[2];                       // [128]: W4[0, 0:128] fp32
     const __half *f_lr, *f_hr;
     int H_lr, W_lr, H_hr, W_hr;
     uint8_t *scratch;                          // 64 KB per CTA
     int64_t ntiles;
+    float w4y[2][128];                         // W4[0, 0:128] of both MLPs (fp32, used in the last epilogue)
 };
 
 // byte offset of 16-byte chunk `chunk` of row `row` inside a [rows x 64] fp16 SWIZZLE_128B block
-__device__ __forceinline__ uint32_t sw128_off(int row, int chunk)
+__host__ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk)
 {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
@@ -93,22 +98,25 @@ __device__ __forceinline__ void accum_tap(float (&acc)[8], uint4 v, float w)
     }
 }
 
-// ---- gather: rows 32*warp .. +31 of the F tile -------------------------------------------
-__device__ __forceinline__ void gather_rows(const PointIO &io, const TcParams &prm, int64_t tile, int warp, int lane,
-                                            uint32_t f_smem, float &zf_out, float &mask_out)
+__device__ __forceinline__ Projected project_row(const PointIO &io, int64_t tile, int row)
 {
-    int64_t n = tile * TILE_M + warp * 32 + lane;
+    int64_t n = tile * TILE_M + row;
     if (n >= io.n) n = io.n - 1;
     float x, y, z;
     pointio_load(io, n, x, y, z);
-    const Projected pr = project_point(io, x, y, z);
-    zf_out = pr.zf;
-    mask_out = pr.mask;
+    return project_point(io, x, y, z);
+}
+
+// ---- gather: warp w fills rows 32*(w%4) + 16*(w/4) .. +15 of the F tile -----------------------
+__device__ __forceinline__ void gather_rows(const PointIO &io, const TcParams &prm, int64_t tile, int warp, int lane, uint32_t f_smem)
+{
+    const int row0 = (warp & 3) * 32 + (warp >> 2) * 16;
+    const Projected pr = project_row(io, tile, row0 + (lane & 15));      // lanes 16-31 mirror lanes 0-15
     const Taps tl = make_taps(pr.u, pr.v, prm.H_lr, prm.W_lr);
     const Taps th = make_taps(pr.u, pr.v, prm.H_hr, prm.W_hr);
     // low-res map: 256 channels = 32 lanes x 8 channels, one point per step
-#pragma unroll 4
-    for (int p = 0; p < 32; ++p) {
+#pragma unroll 8
+    for (int p = 0; p < 16; ++p) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -119,13 +127,12 @@ __device__ __forceinline__ void gather_rows(const PointIO &io, const TcParams &p
                 accum_tap(acc, v, w);
             }
         }
-        const int row = warp * 32 + p;
         const uint4 o = make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7]));
-        st_shared_v4(f_smem + (lane >> 3) * A_BLK_BYTES + sw128_off(row, lane & 7), o);
+        st_shared_v4(f_smem + (lane >> 3) * A_BLK_BYTES + sw128_off(row0 + p, lane & 7), o);
     }
     // high-res map: 64 channels = 8 lanes x 8 channels, four points per step
-#pragma unroll 2
-    for (int it = 0; it < 8; ++it) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
         const int p = it * 4 + (lane >> 3);
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -137,55 +144,52 @@ __device__ __forceinline__ void gather_rows(const PointIO &io, const TcParams &p
                 accum_tap(acc, v, w);
             }
         }
-        const int row = warp * 32 + p;
         const uint4 o = make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7]));
-        st_shared_v4(f_smem + 4 * A_BLK_BYTES + sw128_off(row, lane & 7), o);
+        st_shared_v4(f_smem + 4 * A_BLK_BYTES + sw128_off(row0 + p, lane & 7), o);
     }
 }
 
-// tail block columns: [z_hi, z_lo, pred_hi, pred_lo, 0...]; hi/lo splits keep ~22 bits of the two scalars
+// tail block columns: [z_hi, z_lo, pred_hi, pred_lo, 1, 1, 0, 0 | 0 x 8]; the hi/lo splits keep
+// ~22 bits of the two scalars, the ones multiply the (hi, lo) bias columns of the weight stream
 __device__ __forceinline__ void write_tail(uint32_t f_smem, int row, float zf, float pred)
 {
     const __half zh = __float2half_rn(zf), ph = __float2half_rn(pred);
     const float zl = zf - __half2float(zh), pl = pred - __half2float(ph);
-    const uint4 c0 = make_uint4(pack_h2(__half2float(zh), zl), pack_h2(__half2float(ph), pl), 0u, 0u);
+    const uint4 c0 = make_uint4(pack_h2(__half2float(zh), zl), pack_h2(__half2float(ph), pl), pack_h2(1.0f, 1.0f), 0u);
     st_shared_v4(f_smem + 5 * A_BLK_BYTES + sw128_off(row, 0), c0);
     st_shared_v4(f_smem + 5 * A_BLK_BYTES + sw128_off(row, 1), make_uint4(0u, 0u, 0u, 0u));
 }
 
-// ---- epilogue of a 256-wide accumulator: +bias, leaky_relu, fp16, K-major swizzled store -------
-// dst_smem != 0: into the A operand blocks (hand-off per 64-column block through a_free / a_ready)
-// dst_gmem != 0: into the scratch line (same image, reloaded later by bulk TMA)
-__device__ __forceinline__ void epilogue_256(uint32_t taddr, const float *__restrict__ bias, int row, int lane,
-                                             uint32_t dst_smem, uint8_t *dst_gmem, Bars *bars, uint32_t fill_parity)
+// ---- epilogue of a 256-wide accumulator: leaky_relu, fp16, K-major swizzled store -------------
+// Warp (quarter q, half hsel) converts columns [64 kb + 32 hsel, +32) of rows 32 q.. for kb = 0..3.
+// to_smem: into the A ring (K block g0 + kb -> slot (g0 + kb) % NA_SLOT, hand-off a_free / a_ready);
+// else into the global scratch image (reloaded later by bulk TMA).
+__device__ __forceinline__ void epilogue_256(uint32_t taddr, int row, int hsel, int lane, bool to_smem, uint32_t a_smem,
+                                             uint8_t *dst_gmem, Bars *bars, uint32_t g0, unsigned long long *prof)
 {
-#pragma unroll 1
-    for (int kb = 0; kb < NA_BLK; ++kb) {
-        if (dst_smem) ptx::mbar_wait(&bars->a_free[kb], fill_parity ^ 1u, 10 + kb);
+    uint32_t r[2][32];
+    ptx::tmem_ld32(taddr + hsel * 32, r[0]);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t r[32];
-            ptx::tmem_ld32(taddr + kb * 64 + half * 32, r);
-            ptx::tmem_ld_wait();
+    for (int kb = 0; kb < 4; ++kb) {
+        ptx::tmem_ld_wait();
+        if (kb < 3) ptx::tmem_ld32(taddr + (kb + 1) * 64 + hsel * 32, r[(kb + 1) & 1]);
+        const uint32_t g = g0 + kb, slot = g % NA_SLOT;
+        if (to_smem) ptx::mbar_wait(&bars->a_free[slot], ((g / NA_SLOT) & 1u) ^ 1u, 10, prof);
+        const uint32_t *v = r[kb & 1];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int ch = kb * 64 + half * 32 + j * 8;
-                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + ch));
-                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + ch + 4));
-                const float v0 = leaky(__uint_as_float(r[8 * j + 0]) + b0.x), v1 = leaky(__uint_as_float(r[8 * j + 1]) + b0.y);
-                const float v2 = leaky(__uint_as_float(r[8 * j + 2]) + b0.z), v3 = leaky(__uint_as_float(r[8 * j + 3]) + b0.w);
-                const float v4 = leaky(__uint_as_float(r[8 * j + 4]) + b1.x), v5 = leaky(__uint_as_float(r[8 * j + 5]) + b1.y);
-                const float v6 = leaky(__uint_as_float(r[8 * j + 6]) + b1.z), v7 = leaky(__uint_as_float(r[8 * j + 7]) + b1.w);
-                const uint4 o = make_uint4(pack_h2(v0, v1), pack_h2(v2, v3), pack_h2(v4, v5), pack_h2(v6, v7));
-                const uint32_t off = kb * A_BLK_BYTES + sw128_off(row, half * 4 + j);
-                if (dst_smem) st_shared_v4(dst_smem + off, o);
-                else *reinterpret_cast<uint4 *>(dst_gmem + off) = o;
-            }
+        for (int j = 0; j < 4; ++j) {
+            const uint4 o = make_uint4(pack_h2(leaky(__uint_as_float(v[8 * j + 0])), leaky(__uint_as_float(v[8 * j + 1]))),
+                                       pack_h2(leaky(__uint_as_float(v[8 * j + 2])), leaky(__uint_as_float(v[8 * j + 3]))),
+                                       pack_h2(leaky(__uint_as_float(v[8 * j + 4])), leaky(__uint_as_float(v[8 * j + 5]))),
+                                       pack_h2(leaky(__uint_as_float(v[8 * j + 6])), leaky(__uint_as_float(v[8 * j + 7]))));
+            const uint32_t off = sw128_off(row, hsel * 4 + j);
+            if (to_smem) st_shared_v4(a_smem + slot * A_BLK_BYTES + off, o);
+            else *reinterpret_cast<uint4 *>(dst_gmem + kb * A_BLK_BYTES + off) = o;
         }
-        if (dst_smem) {
+        if (to_smem) {
             ptx::fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&bars->a_ready[kb]);
+            if (lane == 0) ptx::mbar_arrive(&bars->a_ready[slot]);
         }
     }
 }
@@ -199,7 +203,10 @@ __device__ __forceinline__ void mma_block(uint32_t tmem_d, uint32_t a_addr, uint
         ptx::umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (zero_first && k == 0) ? 0u : 1u);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) query_tc_kernel(PointIO io, TcParams prm)
+__device__ unsigned long long g_tc_prof[64];
+
+template <bool PROF>
+__global__ void __launch_bounds__(NTHREADS, 1) query_tc_kernel(const __grid_constant__ PointIO io, const __grid_constant__ TcParams prm)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -208,35 +215,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_tc_kernel(PointIO io, TcPar
     const uint32_t f_smem = base + SMEM_F, a_smem = base + SMEM_A, w_smem = base + SMEM_W;
     Bars *bars = reinterpret_cast<Bars *>(smem + SMEM_BAR);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // profiling build: one designated thread per role accumulates its wait cycles into g_tc_prof[tag]
+    unsigned long long *prof = nullptr;
+    if (PROF && lane == 0 && (warp == 0 || warp >= NEPI)) prof = g_tc_prof;
+    const long long t_kernel0 = PROF ? clock64() : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&bars->full_w[s], 1); ptx::mbar_init(&bars->empty_w[s], 1); }
-        for (int k = 0; k < NA_BLK; ++k) { ptx::mbar_init(&bars->a_ready[k], 4); ptx::mbar_init(&bars->a_free[k], 1); }
-        for (int t = 0; t < 2; ++t) { ptx::mbar_init(&bars->acc_full[t], 1); ptx::mbar_init(&bars->acc_free[t], 4); }
-        ptx::mbar_init(&bars->f_ready, 4);
-        ptx::mbar_init(&bars->scr_ready, 4);
+        for (int k = 0; k < NA_SLOT; ++k) { ptx::mbar_init(&bars->a_ready[k], NEPI); ptx::mbar_init(&bars->a_free[k], 1); }
+        for (int t = 0; t < 2; ++t) { ptx::mbar_init(&bars->acc_full[t], 1); ptx::mbar_init(&bars->acc_free[t], NEPI); }
+        ptx::mbar_init(&bars->f_ready, NEPI);
+        ptx::mbar_init(&bars->scr_ready, NEPI);
         ptx::fence_barrier_init();
     }
-    if (warp == 4) ptx::tmem_alloc(&bars->tmem_base, 512);
+    if (warp == NEPI) ptx::tmem_alloc(&bars->tmem_base, 512);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
     const uint32_t T0 = tmem, T1 = tmem + 256;
-    uint8_t *scratch = prm.scratch + (size_t)blockIdx.x * (NA_BLK * A_BLK_BYTES);
+    uint8_t *scratch = prm.scratch + (size_t)blockIdx.x * (4 * A_BLK_BYTES);
 
-    if (warp < 4) {
+    if (warp < NEPI) {
         // =============================== gather + epilogues ===============================
-        const int row = warp * 32 + lane;
-        const uint32_t lane_t0 = T0 + ((uint32_t)(warp * 32) << 16), lane_t1 = T1 + ((uint32_t)(warp * 32) << 16);
+        const int quarter = warp & 3, hsel = warp >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_t0 = T0 + ((uint32_t)(quarter * 32) << 16), lane_t1 = T1 + ((uint32_t)(quarter * 32) << 16);
         uint32_t afill = 0, acc0 = 0, acc1 = 0;
+        auto release_acc = [&](int t) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars->acc_free[t]);
+        };
         for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
-            float zf, mask;
-            gather_rows(io, prm, tile, warp, lane, f_smem, zf, mask);
-            write_tail(f_smem, row, zf, 0.0f);
+            const long long t_g0 = PROF ? clock64() : 0;
+            gather_rows(io, prm, tile, warp, lane, f_smem);
+            float zf = 0.f, mask = 0.f;
+            if (hsel == 0) {                       // warps 0-3 own the per-row scalars and the tail block
+                const Projected own = project_row(io, tile, row);
+                zf = own.zf;
+                mask = own.mask;
+                write_tail(f_smem, row, zf, 0.0f);
+            }
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&bars->f_ready);
+            if (prof) { atomicAdd(prof + 1, (unsigned long long)(clock64() - t_g0)); atomicAdd(prof + 2, 1ull); }
             float pred_lr = 0.0f;
 #pragma unroll 1
             for (int m = 0; m < 2; ++m) {
@@ -244,95 +268,84 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_tc_kernel(PointIO io, TcPar
                 for (int h = 0; h < 2; ++h) {
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {           // E0: layer-0 chunk -> A
-                        ptx::mbar_wait(&bars->acc_full[0], acc0 & 1u, 20);
+                        ptx::mbar_wait(&bars->acc_full[0], acc0 & 1u, 20, prof);
                         ptx::tc_fence_after();
-                        epilogue_256(lane_t0, prm.bias[m][0] + c * 256, row, lane, a_smem, nullptr, bars, afill & 1u);
+                        epilogue_256(lane_t0, row, hsel, lane, true, a_smem, nullptr, bars, afill * 4, prof);
                         ++afill;
-                        ptx::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&bars->acc_free[0]);
+                        release_acc(0);
                         ++acc0;
                     }
                     // E1: layer-1 half -> scratch (h == 0) or A (h == 1)
-                    ptx::mbar_wait(&bars->acc_full[1], acc1 & 1u, 21);
+                    ptx::mbar_wait(&bars->acc_full[1], acc1 & 1u, 21, prof);
                     ptx::tc_fence_after();
                     if (h == 0) {
-                        epilogue_256(lane_t1, prm.bias[m][1], row, lane, 0u, scratch, bars, 0u);
+                        epilogue_256(lane_t1, row, hsel, lane, false, 0u, scratch, bars, 0u, prof);
                         ptx::fence_proxy_async_all();
                     } else {
-                        epilogue_256(lane_t1, prm.bias[m][1] + 256, row, lane, a_smem, nullptr, bars, afill & 1u);
+                        epilogue_256(lane_t1, row, hsel, lane, true, a_smem, nullptr, bars, afill * 4, prof);
                         ++afill;
                         // Only now may the reload warp start waiting on a_free: mbarrier parity waits
                         // are only meaningful one phase ahead, and its fill is the next one.
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&bars->scr_ready);
                     }
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&bars->acc_free[1]);
+                    release_acc(1);
                     ++acc1;
                 }
-                ++afill;                                    // the reload's fill of A (warp 6)
+                ++afill;                                    // the reload's fill of A (warp NEPI + 2)
                 // E2: layer 2 -> A
-                ptx::mbar_wait(&bars->acc_full[0], acc0 & 1u, 22);
+                ptx::mbar_wait(&bars->acc_full[0], acc0 & 1u, 22, prof);
                 ptx::tc_fence_after();
-                epilogue_256(lane_t0, prm.bias[m][2], row, lane, a_smem, nullptr, bars, afill & 1u);
+                epilogue_256(lane_t0, row, hsel, lane, true, a_smem, nullptr, bars, afill * 4, prof);
                 ++afill;
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&bars->acc_free[0]);
+                release_acc(0);
                 ++acc0;
-                // E3: layer 3 + layer 4 + sigmoid
-                ptx::mbar_wait(&bars->acc_full[1], acc1 & 1u, 23);
+                // E3: layer 3 + layer 4 + sigmoid (warps 0-3; the others only hand the accumulator back)
+                ptx::mbar_wait(&bars->acc_full[1], acc1 & 1u, 23, prof);
                 ptx::tc_fence_after();
-                float logit = __ldg(prm.bias[m][4]);
+                float logit = 0.0f;
+                if (hsel == 0) {
 #pragma unroll 1
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t r[32];
-                    ptx::tmem_ld32(lane_t1 + q * 32, r);
-                    ptx::tmem_ld_wait();
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t r[32];
+                        ptx::tmem_ld32(lane_t1 + q * 32, r);
+                        ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4 *>(prm.bias[m][3] + q * 32 + j));
-                        const float4 w = __ldg(reinterpret_cast<const float4 *>(prm.w4y[m] + q * 32 + j));
-                        logit = fmaf(w.x, leaky(__uint_as_float(r[j]) + b.x), logit);
-                        logit = fmaf(w.y, leaky(__uint_as_float(r[j + 1]) + b.y), logit);
-                        logit = fmaf(w.z, leaky(__uint_as_float(r[j + 2]) + b.z), logit);
-                        logit = fmaf(w.w, leaky(__uint_as_float(r[j + 3]) + b.w), logit);
+                        for (int j = 0; j < 32; ++j) logit = fmaf(prm.w4y[m][q * 32 + j], leaky(__uint_as_float(r[j])), logit);
                     }
-                }
-                {
                     uint32_t r[32];
-                    ptx::tmem_ld32(lane_t1 + 128, r);       // column 128 = W4's skip part . f
+                    ptx::tmem_ld32(lane_t1 + 128, r);       // column 128 = W4's skip part . f + b4
                     ptx::tmem_ld_wait();
                     logit += __uint_as_float(r[0]);
                 }
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&bars->acc_free[1]);
+                release_acc(1);
                 ++acc1;
-                const float pred = mask * (1.0f / (1.0f + expf(-logit)));
+                if (hsel == 0) {
+                    const float pred = mask * (1.0f / (1.0f + expf(-logit)));
+                    if (m == 0) {
+                        pred_lr = pred;
+                        write_tail(f_smem, row, zf, pred);  // SuRSNet.py:180: the MASKED pred_lr is channel 321
+                        ptx::fence_proxy_async_smem();
+                    } else {
+                        const int64_t n = tile * TILE_M + row;
+                        if (n < io.n) pointio_store(io, n, pred, pred_lr);
+                    }
+                }
                 if (m == 0) {
-                    pred_lr = pred;
-                    write_tail(f_smem, row, zf, pred);      // SuRSNet.py:180: the MASKED pred_lr is channel 321
-                    ptx::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&bars->f_ready);
-                } else {
-                    const int64_t n = tile * TILE_M + row;
-                    if (n < io.n) pointio_store(io, n, pred, pred_lr);
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == NEPI) {
         // =============================== MMA issue ========================================
         if (lane == 0) {
             constexpr uint32_t IDESC256 = ptx::umma_idesc_f16(128, 256);
             constexpr uint32_t IDESC144 = ptx::umma_idesc_f16(128, W3_ROWS);
-            uint32_t wblk = 0, afill = 0, acc0 = 0, acc1 = 0, fcnt = 0;
+            uint32_t wblk = 0, ablk = 0, acc0 = 0, acc1 = 0, fcnt = 0;
             auto wait_w = [&]() -> uint32_t {
                 const uint32_t s = wblk % NSTAGE;
-                ptx::mbar_wait(&bars->full_w[s], (wblk / NSTAGE) & 1u, 30);
+                ptx::mbar_wait(&bars->full_w[s], (wblk / NSTAGE) & 1u, 30, prof);
                 ptx::tc_fence_after();
                 return w_smem + s * W_BLK_BYTES;
             };
@@ -348,48 +361,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_tc_kernel(PointIO io, TcPar
                     release_w();
                 }
             };
-            // accumulate the A operand (4 blocks) into tmem_d; hands each block back through a_free
+            // only the tail block of F (bias of a layer whose input is not F)
+            auto mma_F_tail = [&](uint32_t tmem_d, uint32_t idesc) {
+                const uint32_t w = wait_w();
+                mma_block(tmem_d, f_smem + (NF_BLK - 1) * A_BLK_BYTES, w, 1, idesc, false);
+                release_w();
+            };
+            // accumulate 4 K blocks of the A ring into tmem_d; hands each slot back through a_free
             auto mma_A = [&](uint32_t tmem_d, uint32_t idesc, bool zero_first) {
-                for (int kb = 0; kb < NA_BLK; ++kb) {
-                    ptx::mbar_wait(&bars->a_ready[kb], afill & 1u, 31);
+                for (int kb = 0; kb < 4; ++kb) {
+                    const uint32_t slot = ablk % NA_SLOT;
+                    ptx::mbar_wait(&bars->a_ready[slot], (ablk / NA_SLOT) & 1u, 31, prof);
+                    ptx::tc_fence_after();
                     const uint32_t w = wait_w();
-                    mma_block(tmem_d, a_smem + kb * A_BLK_BYTES, w, 4, idesc, zero_first && kb == 0);
+                    mma_block(tmem_d, a_smem + slot * A_BLK_BYTES, w, 4, idesc, zero_first && kb == 0);
                     release_w();
-                    ptx::umma_commit(&bars->a_free[kb]);
+                    ptx::umma_commit(&bars->a_free[slot]);
+                    ++ablk;
                 }
-                ++afill;
             };
             for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
                 for (int m = 0; m < 2; ++m) {
-                    ptx::mbar_wait(&bars->f_ready, fcnt & 1u, 32);     // gather done / pred_lr written
+                    ptx::mbar_wait(&bars->f_ready, fcnt & 1u, 32, prof);     // gather done / pred_lr written
                     ++fcnt;
                     ptx::tc_fence_after();
                     for (int h = 0; h < 2; ++h) {
                         for (int c = 0; c < 4; ++c) {
-                            ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 33);
+                            ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 33, prof);
                             ptx::tc_fence_after();
-                            mma_F(T0, IDESC256, true);                  // layer 0, chunk c
+                            mma_F(T0, IDESC256, true);                  // layer 0, chunk c (+ b0)
                             ptx::umma_commit(&bars->acc_full[0]);
                             ++acc0;
                             if (c == 0) {
-                                ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 34);
+                                ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 34, prof);
                                 ptx::tc_fence_after();
                             }
                             mma_A(T1, IDESC256, c == 0);                // layer 1, half h, K chunk c
                         }
+                        mma_F_tail(T1, IDESC256);                       // + b1 (half h)
                         ptx::umma_commit(&bars->acc_full[1]);
                         ++acc1;
                     }
-                    // layer 2 = W2[:, 256:512] y1[1] + W2[:, 0:256] y1[0] + W2[:, 512:] f
-                    ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 35);
+                    // layer 2 = W2[:, 256:512] y1[1] + W2[:, 0:256] y1[0] + W2[:, 512:] f (+ b2)
+                    ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 35, prof);
                     ptx::tc_fence_after();
                     mma_A(T0, IDESC256, true);
                     mma_A(T0, IDESC256, false);
                     mma_F(T0, IDESC256, false);
                     ptx::umma_commit(&bars->acc_full[0]);
                     ++acc0;
-                    // layer 3 (+ W4's skip row) = W3[:, 0:256] y2 + W3[:, 256:] f
-                    ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 36);
+                    // layer 3 (+ W4's skip row) = W3[:, 0:256] y2 + W3[:, 256:] f (+ b3, b4)
+                    ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 36, prof);
                     ptx::tc_fence_after();
                     mma_A(T1, IDESC144, true);
                     mma_F(T1, IDESC144, false);
@@ -398,7 +420,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_tc_kernel(PointIO io, TcPar
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == NEPI + 1) {
         // =============================== weight stream ====================================
         if (lane == 0) {
             uint32_t wblk = 0;
@@ -407,7 +429,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_tc_kernel(PointIO io, TcPar
                 for (int b = 0; b < 2 * BLOCKS_PER_MLP; ++b) {
                     const uint32_t bytes = (b % BLOCKS_PER_MLP) < N256_BLOCKS_PER_MLP ? W_BLK_BYTES : W3_BLK_BYTES;
                     const uint32_t s = wblk % NSTAGE;
-                    ptx::mbar_wait(&bars->empty_w[s], ((wblk / NSTAGE) & 1u) ^ 1u, 40);
+                    ptx::mbar_wait(&bars->empty_w[s], ((wblk / NSTAGE) & 1u) ^ 1u, 40, prof);
                     ptx::mbar_arrive_expect_tx(&bars->full_w[s], bytes);
                     ptx::tma_load_1d(smem + SMEM_W + s * W_BLK_BYTES, src, bytes, &bars->full_w[s]);
                     src += bytes;
@@ -421,49 +443,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_tc_kernel(PointIO io, TcPar
             uint32_t scr = 0, tiles_done = 0;
             for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tiles_done) {
                 for (int m = 0; m < 2; ++m) {
-                    // this is fill number 9 (0-based) of the MLP's 11 fills of A
-                    const uint32_t fill = (tiles_done * 2 + m) * A_FILLS_PER_MLP + 9;
-                    ptx::mbar_wait(&bars->scr_ready, scr & 1u, 50);
+                    // fill number 9 (0-based) of the MLP's 11 fills of A = K blocks 36..39 of its 44
+                    const uint32_t g0 = ((tiles_done * 2 + m) * A_FILLS_PER_MLP + 9) * 4;
+                    ptx::mbar_wait(&bars->scr_ready, scr & 1u, 50, prof);
                     ++scr;
-                    for (int kb = 0; kb < NA_BLK; ++kb) {
-                        ptx::mbar_wait(&bars->a_free[kb], (fill & 1u) ^ 1u, 51);
-                        ptx::mbar_arrive_expect_tx(&bars->a_ready[kb], A_BLK_BYTES);
-                        ptx::mbar_arrive(&bars->a_ready[kb]);
-                        ptx::mbar_arrive(&bars->a_ready[kb]);
-                        ptx::mbar_arrive(&bars->a_ready[kb]);
-                        ptx::tma_load_1d(smem + SMEM_A + kb * A_BLK_BYTES, scratch + kb * A_BLK_BYTES, A_BLK_BYTES, &bars->a_ready[kb]);
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint32_t g = g0 + kb, slot = g % NA_SLOT;
+                        ptx::mbar_wait(&bars->a_free[slot], ((g / NA_SLOT) & 1u) ^ 1u, 51, prof);
+                        ptx::mbar_arrive_expect_tx(&bars->a_ready[slot], A_BLK_BYTES);
+                        for (int i = 1; i < NEPI; ++i) ptx::mbar_arrive(&bars->a_ready[slot]);
+                        ptx::tma_load_1d(smem + SMEM_A + slot * A_BLK_BYTES, scratch + kb * A_BLK_BYTES, A_BLK_BYTES, &bars->a_ready[slot]);
                     }
                 }
             }
         }
     }
+    if (PROF && threadIdx.x == 0) atomicAdd(g_tc_prof + 0, (unsigned long long)(clock64() - t_kernel0));
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 4) ptx::tmem_dealloc(tmem, 512);
+    if (warp == NEPI) ptx::tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------
-// weight packing: fp32 [Cout, Cin] -> the block stream consumed above
+// weight packing: fp32 [Cout, Cin] (+ bias) -> the block stream consumed above
 // ------------------------------------------------------------------------------------------
 struct PackDesc {
     const float *w;        // source layer, row-major [cout][cin]
     const float *w_extra;  // layer 4 (row 128 of the layer-3 skip blocks) or NULL
-    int cin, cin_extra;
+    const float *bias;     // bias of the rows (tail blocks only) or NULL
+    const float *bias_extra;
+    int cin;
     int row0, nrows;       // rows taken from w; the block has ntotal rows, the rest is zero
     int ntotal;
     int fblock;            // -1: plain columns k0 .. k0+63; else F-order block index 0..5
+    int bias_only;         // tail block that carries nothing but the bias (layer 1)
     int k0, k0_extra;      // first column (plain) / start of the skip part (F-order)
     int c0;                // 321 / 322: width of the skip input
     uint32_t out_off;
 };
 
-// column of the skip input that F-tile position (fblock, kk) holds, or -1 for padding
+// column of the skip input that F-tile position (fblock, kk) holds; -1 padding, -2 / -3 bias hi / lo
 __device__ __forceinline__ int fmap(int fblock, int kk, int c0)
 {
     if (fblock < 4) return fblock * 64 + kk;
     if (fblock == 4) return 256 + kk;
     if (kk < 2) return 320;                      // z_hi, z_lo
     if (kk < 4) return c0 > 321 ? 321 : -1;      // pred_hi, pred_lo (HR MLP only)
+    if (kk == 4) return -2;
+    if (kk == 5) return -3;
     return -1;
 }
 
@@ -484,9 +511,15 @@ __global__ void pack_weights_kernel(const PackDesc *descs, uint8_t *out)
                     if (r < d.nrows) x = d.w[(size_t)(d.row0 + r) * d.cin + d.k0 + kk];
                 } else {
                     const int col = fmap(d.fblock, kk, d.c0);
-                    if (col >= 0) {
+                    if (col >= 0 && !d.bias_only) {
                         if (r < d.nrows) x = d.w[(size_t)(d.row0 + r) * d.cin + d.k0 + col];
                         else if (r == 128 && d.w_extra) x = d.w_extra[d.k0_extra + col];
+                    } else if (col <= -2) {
+                        float b = 0.0f;
+                        if (r < d.nrows && d.bias) b = d.bias[d.row0 + r];
+                        else if (r == 128 && d.bias_extra) b = d.bias_extra[0];
+                        const float hi = __half2float(__float2half_rn(b));
+                        x = col == -2 ? hi : b - hi;
                     }
                 }
                 v[j] = x;
@@ -495,11 +528,6 @@ __global__ void pack_weights_kernel(const PackDesc *descs, uint8_t *out)
         }
         *reinterpret_cast<uint4 *>(out + d.out_off + sw128_off(r, c)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
-}
-
-__global__ void copy_w4y_kernel(const float *w4, float *dst)
-{
-    if (threadIdx.x < 128) dst[threadIdx.x] = w4[threadIdx.x];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -568,7 +596,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float *A, c
 
 int surs_tc_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS], cudaStream_t st)
 {
-    const size_t total = 2 * MLP_BYTES + 2 * 128 * sizeof(float);
+    const size_t total = 2 * MLP_BYTES;
     if (!ctx->tc_weights) {
         SURS_CUDA(ctx, cudaMalloc(&ctx->tc_weights, total));
         ctx->tc_weights_bytes = total;
@@ -578,29 +606,33 @@ int surs_tc_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS]
     for (int m = 0; m < 2; ++m) {
         const int c0 = m == 0 ? SURS_C0_LR : SURS_C0_HR;
         uint32_t off = (uint32_t)(m * MLP_BYTES);
-        auto add = [&](int layer, int row0, int nrows, int ntotal, int fblock, int k0, bool extra) {
+        auto add = [&](int layer, int row0, int nrows, int ntotal, int fblock, int k0, bool extra, bool bias_only) {
             PackDesc d;
             memset(&d, 0, sizeof(d));
             d.w = w[m][layer];
             d.cin = ctx->cin[m][layer];
             d.w_extra = extra ? w[m][4] : nullptr;
-            d.cin_extra = ctx->cin[m][4];
+            d.bias = ctx->b32[m][layer];
+            d.bias_extra = extra ? ctx->b32[m][4] : nullptr;
             d.k0_extra = 128;
             d.row0 = row0; d.nrows = nrows; d.ntotal = ntotal; d.fblock = fblock; d.k0 = k0; d.c0 = c0;
+            d.bias_only = bias_only ? 1 : 0;
             d.out_off = off;
             off += (uint32_t)ntotal * 128u;
             host[n++] = d;
         };
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h) {
             for (int c = 0; c < 4; ++c) {
-                for (int kb = 0; kb < NF_BLK; ++kb) add(0, c * 256, 256, 256, kb, 0, false);          // layer 0 chunk c
-                for (int kb = 0; kb < NA_BLK; ++kb) add(1, h * 256, 256, 256, -1, c * 256 + kb * 64, false);   // layer 1
+                for (int kb = 0; kb < NF_BLK; ++kb) add(0, c * 256, 256, 256, kb, 0, false, false);            // layer 0 chunk c
+                for (int kb = 0; kb < 4; ++kb) add(1, h * 256, 256, 256, -1, c * 256 + kb * 64, false, false);   // layer 1
             }
-        for (int kb = 0; kb < NA_BLK; ++kb) add(2, 0, 256, 256, -1, 256 + kb * 64, false);           // y1[1]
-        for (int kb = 0; kb < NA_BLK; ++kb) add(2, 0, 256, 256, -1, kb * 64, false);                 // y1[0]
-        for (int kb = 0; kb < NF_BLK; ++kb) add(2, 0, 256, 256, kb, 512, false);                     // skip
-        for (int kb = 0; kb < NA_BLK; ++kb) add(3, 0, 128, W3_ROWS, -1, kb * 64, false);             // y2
-        for (int kb = 0; kb < NF_BLK; ++kb) add(3, 0, 128, W3_ROWS, kb, 256, true);                  // skip + W4 row
+            add(1, h * 256, 256, 256, NF_BLK - 1, 0, false, true);                                             // b1
+        }
+        for (int kb = 0; kb < 4; ++kb) add(2, 0, 256, 256, -1, 256 + kb * 64, false, false);        // y1[1]
+        for (int kb = 0; kb < 4; ++kb) add(2, 0, 256, 256, -1, kb * 64, false, false);              // y1[0]
+        for (int kb = 0; kb < NF_BLK; ++kb) add(2, 0, 256, 256, kb, 512, false, false);             // skip (+ b2)
+        for (int kb = 0; kb < 4; ++kb) add(3, 0, 128, W3_ROWS, -1, kb * 64, false, false);          // y2
+        for (int kb = 0; kb < NF_BLK; ++kb) add(3, 0, 128, W3_ROWS, kb, 256, true, false);          // skip + W4 row (+ b3, b4)
         if (off != (uint32_t)((m + 1) * MLP_BYTES)) SURS_FAIL(ctx, "internal: weight stream size mismatch");
     }
     PackDesc *dev = nullptr;
@@ -608,11 +640,8 @@ int surs_tc_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS]
     SURS_CUDA(ctx, cudaMemcpyAsync(dev, host, sizeof(host), cudaMemcpyHostToDevice, st));
     pack_weights_kernel<<<n, 256, 0, st>>>(dev, (uint8_t *)ctx->tc_weights);
     SURS_LAUNCH_CHECK(ctx, "pack_weights_kernel");
-    float *w4y = reinterpret_cast<float *>((uint8_t *)ctx->tc_weights + 2 * MLP_BYTES);
-    for (int m = 0; m < 2; ++m) {
-        copy_w4y_kernel<<<1, 128, 0, st>>>(w[m][4], w4y + 128 * m);
-        SURS_LAUNCH_CHECK(ctx, "copy_w4y_kernel");
-    }
+    for (int m = 0; m < 2; ++m)
+        SURS_CUDA(ctx, cudaMemcpyAsync(ctx->tc_w4y[m], w[m][4], 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
     SURS_CUDA(ctx, cudaStreamSynchronize(st));
     SURS_CUDA(ctx, cudaFree(dev));
     return 0;
@@ -623,20 +652,33 @@ int surs_launch_query_tc(surs_ctx *ctx, const PointIO &io, cudaStream_t st)
     if (io.n <= 0) return 0;
     TcParams prm;
     prm.weights = (const uint8_t *)ctx->tc_weights;
-    const float *w4y = reinterpret_cast<const float *>((const uint8_t *)ctx->tc_weights + 2 * MLP_BYTES);
-    for (int m = 0; m < 2; ++m) {
-        for (int l = 0; l < SURS_NUM_LAYERS; ++l) prm.bias[m][l] = ctx->b32[m][l];
-        prm.w4y[m] = w4y + 128 * m;
-    }
+    memcpy(prm.w4y, ctx->tc_w4y, sizeof(prm.w4y));
     prm.f_lr = ctx->f_lr16; prm.f_hr = ctx->f_hr16;
     prm.H_lr = ctx->H_lr; prm.W_lr = ctx->W_lr; prm.H_hr = ctx->H_hr; prm.W_hr = ctx->W_hr;
     prm.ntiles = (io.n + TILE_M - 1) / TILE_M;
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
-    if (surs_ensure(ctx, (void **)&ctx->tc_scratch, &ctx->tc_scratch_cap, (size_t)ctx->sm_count * NA_BLK * A_BLK_BYTES)) return 1;
+    if (surs_ensure(ctx, (void **)&ctx->tc_scratch, &ctx->tc_scratch_cap, (size_t)ctx->sm_count * 4 * A_BLK_BYTES)) return 1;
     prm.scratch = (uint8_t *)ctx->tc_scratch;
-    SURS_CUDA(ctx, cudaFuncSetAttribute(query_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    query_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
-    SURS_LAUNCH_CHECK(ctx, "query_tc_kernel");
+    static const bool profile = getenv("SURS_TC_PROFILE") != nullptr;
+    if (!profile) {
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        query_tc_kernel<false><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+        SURS_LAUNCH_CHECK(ctx, "query_tc_kernel");
+        return 0;
+    }
+    // SURS_TC_PROFILE=1: synchronous launch of the instrumented kernel + a table of wait cycles per role
+    unsigned long long zero[64] = {0}, h[64];
+    SURS_CUDA(ctx, cudaMemcpyToSymbol(g_tc_prof, zero, sizeof(zero)));
+    SURS_CUDA(ctx, cudaFuncSetAttribute(query_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    query_tc_kernel<true><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+    SURS_LAUNCH_CHECK(ctx, "query_tc_kernel<profile>");
+    SURS_CUDA(ctx, cudaStreamSynchronize(st));
+    SURS_CUDA(ctx, cudaMemcpyFromSymbol(h, g_tc_prof, sizeof(h)));
+    const double tiles = (double)(h[2] ? h[2] : 1), k = 1e-3 / tiles;
+    fprintf(stderr, "[surs tc profile] tiles=%llu grid=%d kcycles/tile: total %.1f | epi warp0: gather %.1f wait_acc_full(E0 %.1f E1 %.1f E2 %.1f E3 %.1f) "
+                    "wait_a_free %.1f | mma: wait_w %.1f wait_a_ready %.1f wait_f %.1f wait_acc_free(%.1f %.1f %.1f %.1f) | loader wait_empty %.1f | reload %.1f %.1f\n",
+            h[2], grid, h[0] * k, h[1] * k, h[20] * k, h[21] * k, h[22] * k, h[23] * k, h[10] * k,
+            h[30] * k, h[31] * k, h[32] * k, h[33] * k, h[34] * k, h[35] * k, h[36] * k, h[40] * k, h[50] * k, h[51] * k);
     return 0;
 }
 
