@@ -1,0 +1,76 @@
+"""Host-side logic of the slab-parallel reconstruction (surs_b200/parallel.py) on CPU:
+plane partitioning, offsets, and the two exchanges (variable-length gather, seam pass-up) with
+world_size 2 over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from surs_b200 import parallel
+
+
+def test_slab_ranges_cover_all_cells_once():
+    for planes in (2, 3, 17, 128, 512):
+        for world in (1, 2, 3, 4, 8):
+            if planes - 1 < world:
+                continue
+            r = parallel.slab_ranges(planes, world)
+            assert r[0][0] == 0 and r[-1][1] == planes
+            cells = []
+            for k, (lo, hi) in enumerate(r):
+                last = hi if k < world - 1 else hi - 1       # a cell is owned by the rank owning its lower plane
+                cells.extend(range(lo, last))
+                assert hi > lo
+            assert cells == list(range(planes - 1))
+            sizes = [hi - lo for lo, hi in r[:-1]] + [r[-1][1] - 1 - r[-1][0]]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_exclusive_offsets():
+    off = parallel.exclusive_offsets([[3, 5], [0, 2], [7, 1]])
+    assert off.tolist() == [[0, 0], [3, 5], [3, 7]]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        counts = [5, 0, 3][:world] if world == 3 else [4, 7]
+        local = torch.arange(counts[rank] * 3, dtype=torch.float32).reshape(counts[rank], 3) + 100 * rank
+        got = parallel.gather_rows(local, counts, 0)
+        seam_out = torch.full((2, 4, 4), rank, dtype=torch.int32)
+        seam_in = torch.full((2, 4, 4), -7, dtype=torch.int32)
+        parallel.pass_up(seam_out, seam_in)
+        if rank == 0:
+            want = torch.cat([torch.arange(c * 3, dtype=torch.float32).reshape(c, 3) + 100 * r for r, c in enumerate(counts)])
+            ok = torch.equal(got, want) and bool((seam_in == -7).all())
+        else:
+            ok = got is None and bool((seam_in == rank - 1).all())
+        out.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_and_seam_exchange_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
