@@ -1,0 +1,678 @@
+// Column-factored dense grid evaluation (SURS_PREC_FP16, surs_eval_grid without a transform).
+//
+// With the calibration used by gen_mesh (lib/train_util.py:63-66: diag(2,-2,2,1)) -- in general
+// whenever calib[0][2] == calib[1][2] == 0 and the grid is not transformed -- the image
+// coordinates (u,v) of a grid node depend only on its (i,j) and all 320 gathered feature
+// channels are identical along a k-column (lib/sdf.py:17-24 + lib/geometry.py:15-31).  Every
+// product of a weight matrix with the image features is therefore computed ONCE PER COLUMN:
+//
+//   table kernel  (col_table_kernel): for each column, C0 = W0[:, :320] f + b0 (1024),
+//       C2 = W2[:, 512:832] f + b2 (256), C3 = W3[:, 256:576] f + b3 (128),
+//       C4 = W4[:, 128:448] f + b4 (1), for both MLPs -- a tcgen05 GEMM over 128-column tiles.
+//   main kernel   (query_col_kernel): tile = 128 consecutive k of one column.  Layer 0 collapses
+//       to y0 = leaky(C0 + w_z z_feat (+ w_p pred_lr)) on the CUDA cores; layers 1-3 run on the
+//       tensor cores exactly as in query_tc.cu but without layer-0 / skip GEMMs:
+//       L1 (K=1024, N=512: both TMEM accumulators), L2 (K=512, N=256), L3 (K=256, N=128);
+//       the skip terms enter the epilogues as C2 / C3 / C4 + rank-1 updates in z_feat and pred_lr.
+//
+// Identical arithmetic up to rounding order (it is an exact refactoring of W.[y; f; z; p]),
+// executed MACs per point drop from 3.0 M (query_tc.cu) to 1.38 M and the weight stream per tile
+// from 6.7 MB to 2.7 MB.  The algorithmic FLOP count used for roofline reporting stays
+// 4 564 998 per point.
+//
+// Warp roles (main kernel): 0-7 produce y0 and run the epilogues (warp w: TMEM lanes 32 (w%4)..,
+// column half w/4), 8 = MMA issue, 9 = weight stream + per-column vectors (bulk TMA).
+#include "tc_common.cuh"
+
+#include <stdlib.h>
+
+namespace {
+
+using namespace tc;
+
+// ---- per-column vectors (fp32), per MLP ---------------------------------------------------
+constexpr int CV_C0 = 0, CV_C2 = 1024, CV_C3 = 1280, CV_C4 = 1408, CV_STRIDE = 1412;
+constexpr int CV_FLOATS = 2 * CV_STRIDE;                 // both MLPs
+constexpr int CV_BYTES = CV_FLOATS * 4;                  // 11296 B per column
+// ---- per-MLP constant vectors (fp32) --------------------------------------------------------
+constexpr int GV_WZ0 = 0, GV_WP0 = 1024, GV_B1 = 2048, GV_WZ2 = 2560, GV_WP2 = 2816, GV_WZ3 = 3072, GV_WP3 = 3200,
+              GV_W4Y = 3328, GV_WZ4 = 3456, GV_WP4 = 3457, GV_STRIDE = 3460;
+constexpr int GV_BYTES = 2 * GV_STRIDE * 4;              // 27680 B
+
+constexpr int W128_BLK_BYTES = 128 * 128;                // layer 3: 128 rows x 64 fp16
+constexpr int NSTAGE = 4;
+constexpr int NA_SLOT = 3;
+constexpr int BLOCKS_PER_MLP = 32 + 8 + 4;
+constexpr size_t MLP_BYTES = (size_t)40 * W_BLK_BYTES + 4 * (size_t)W128_BLK_BYTES;
+constexpr int KBLK_PER_MLP = 16 + 4 + 4 + 4;             // A-ring K blocks per MLP
+constexpr int NEPI = 8;
+constexpr int NTHREADS = (NEPI + 2) * 32;
+
+constexpr int SMEM_W = 0;
+constexpr int SMEM_A = SMEM_W + NSTAGE * W_BLK_BYTES;
+constexpr int SMEM_CV = SMEM_A + NA_SLOT * A_BLK_BYTES;
+constexpr int SMEM_GV = SMEM_CV + 2 * CV_BYTES;
+constexpr int SMEM_BAR = SMEM_GV + GV_BYTES;
+constexpr int SMEM_PREDX = SMEM_BAR + 256;               // pred_lr hand-over between the two warps of a quarter
+constexpr int SMEM_TOTAL = SMEM_PREDX + 512 + 1024;
+static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
+
+struct Bars {
+    uint64_t full_w[NSTAGE], empty_w[NSTAGE];
+    uint64_t a_ready[NA_SLOT], a_free[NA_SLOT];
+    uint64_t acc_full[2], acc_free[2];
+    uint64_t cv_full[2], cv_empty[2];
+    uint32_t tmem_base;
+};
+
+struct ColParams {
+    const uint8_t *weights;        // 2 x MLP_BYTES
+    const float *gv;               // [2][GV_STRIDE]
+    const float *table;            // [ncols][CV_FLOATS]
+    int64_t ntiles;
+    int nseg;                      // tiles per column = ceil(R2 / 128)
+    int R1, R2, plane_lo;
+};
+
+// 32 consecutive channels of one row -> fp16 -> A ring slot.  v = acc + add + wz * zf + wp * pred.
+template <bool HAS_ACC, bool HAS_Z, bool HAS_P>
+__device__ __forceinline__ void finish32(const uint32_t *acc, const float *add, const float *wz, const float *wp,
+                                         float zf, float pred, uint32_t dst, int row, int hsel)
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float4 a = *reinterpret_cast<const float4 *>(add + 8 * j + 4 * q);
+            v[4 * q + 0] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+            if (HAS_Z) {
+                const float4 z = *reinterpret_cast<const float4 *>(wz + 8 * j + 4 * q);
+                v[4 * q + 0] = fmaf(z.x, zf, v[4 * q + 0]); v[4 * q + 1] = fmaf(z.y, zf, v[4 * q + 1]);
+                v[4 * q + 2] = fmaf(z.z, zf, v[4 * q + 2]); v[4 * q + 3] = fmaf(z.w, zf, v[4 * q + 3]);
+            }
+            if (HAS_P) {
+                const float4 p = *reinterpret_cast<const float4 *>(wp + 8 * j + 4 * q);
+                v[4 * q + 0] = fmaf(p.x, pred, v[4 * q + 0]); v[4 * q + 1] = fmaf(p.y, pred, v[4 * q + 1]);
+                v[4 * q + 2] = fmaf(p.z, pred, v[4 * q + 2]); v[4 * q + 3] = fmaf(p.w, pred, v[4 * q + 3]);
+            }
+        }
+        if (HAS_ACC) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += __uint_as_float(acc[8 * j + i]);
+        }
+        const uint4 o = make_uint4(pack_h2(leaky(v[0]), leaky(v[1])), pack_h2(leaky(v[2]), leaky(v[3])),
+                                   pack_h2(leaky(v[4]), leaky(v[5])), pack_h2(leaky(v[6]), leaky(v[7])));
+        st_shared_v4(dst + sw128_off(row, hsel * 4 + j), o);
+    }
+}
+
+struct EpiCtx {
+    Bars *bars;
+    uint32_t a_smem;
+    int row, hsel, lane;
+    float zf, pred;
+    uint32_t g;                    // running A-ring K block number
+    unsigned long long *prof;
+};
+
+__device__ __forceinline__ uint32_t ring_acquire(EpiCtx &e)
+{
+    const uint32_t slot = e.g % NA_SLOT;
+    ptx::mbar_wait(&e.bars->a_free[slot], ((e.g / NA_SLOT) & 1u) ^ 1u, 10, e.prof);
+    return slot;
+}
+__device__ __forceinline__ void ring_publish(EpiCtx &e, uint32_t slot)
+{
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (e.lane == 0) ptx::mbar_arrive(&e.bars->a_ready[slot]);
+    ++e.g;
+}
+
+// epilogue of a 256-column accumulator into 4 K blocks of the A ring; the accumulator is handed
+// back (acc_free) as soon as its last column has been read, before the last block is written
+template <bool HAS_Z, bool HAS_P>
+__device__ __forceinline__ void epilogue_256(EpiCtx &e, uint32_t taddr, int acc_id, const float *add, const float *wz, const float *wp)
+{
+    uint32_t r[2][32];
+    ptx::tmem_ld32(taddr + e.hsel * 32, r[0]);
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+        ptx::tmem_ld_wait();
+        if (kb < 3) {
+            ptx::tmem_ld32(taddr + (kb + 1) * 64 + e.hsel * 32, r[(kb + 1) & 1]);
+        } else {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (e.lane == 0) ptx::mbar_arrive(&e.bars->acc_free[acc_id]);
+        }
+        const uint32_t slot = ring_acquire(e);
+        const int c = kb * 64 + e.hsel * 32;
+        finish32<true, HAS_Z, HAS_P>(r[kb & 1], add + c, wz + c, wp + c, e.zf, e.pred, e.a_smem + slot * A_BLK_BYTES, e.row, e.hsel);
+        ring_publish(e, slot);
+    }
+}
+
+__device__ unsigned long long g_col_prof[64];
+
+template <bool PROF>
+__global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_constant__ PointIO io, const __grid_constant__ ColParams prm)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (base - raw);
+    const uint32_t a_smem = base + SMEM_A, w_smem = base + SMEM_W;
+    float *cv_s = reinterpret_cast<float *>(smem + SMEM_CV);
+    float *gv_s = reinterpret_cast<float *>(smem + SMEM_GV);
+    Bars *bars = reinterpret_cast<Bars *>(smem + SMEM_BAR);
+    float *pred_x = reinterpret_cast<float *>(smem + SMEM_PREDX);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long *prof = nullptr;
+    if (PROF && lane == 0 && (warp == 0 || warp >= NEPI)) prof = g_col_prof;
+    const long long t_kernel0 = PROF ? clock64() : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&bars->full_w[s], 1); ptx::mbar_init(&bars->empty_w[s], 1); }
+        for (int k = 0; k < NA_SLOT; ++k) { ptx::mbar_init(&bars->a_ready[k], NEPI); ptx::mbar_init(&bars->a_free[k], 1); }
+        for (int t = 0; t < 2; ++t) {
+            ptx::mbar_init(&bars->acc_full[t], 1); ptx::mbar_init(&bars->acc_free[t], NEPI);
+            ptx::mbar_init(&bars->cv_full[t], 1); ptx::mbar_init(&bars->cv_empty[t], NEPI);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == NEPI) ptx::tmem_alloc(&bars->tmem_base, 512);
+    for (int i = threadIdx.x; i < GV_BYTES / 16; i += NTHREADS)          // constant vectors: resident for the whole kernel
+        reinterpret_cast<uint4 *>(gv_s)[i] = __ldg(reinterpret_cast<const uint4 *>(prm.gv) + i);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    const uint32_t T0 = tmem, T1 = tmem + 256;
+
+    if (warp < NEPI) {
+        // =============================== y0 production + epilogues ========================
+        EpiCtx e;
+        e.bars = bars; e.a_smem = a_smem; e.lane = lane; e.prof = prof; e.g = 0;
+        const int quarter = warp & 3;
+        e.hsel = warp >> 2;
+        e.row = quarter * 32 + lane;
+        const uint32_t lane_t0 = T0 + ((uint32_t)(quarter * 32) << 16), lane_t1 = T1 + ((uint32_t)(quarter * 32) << 16);
+        uint32_t acc0 = 0, acc1 = 0, it = 0;
+        for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++it) {
+            const int64_t col = tile / prm.nseg;
+            const int seg = (int)(tile - col * prm.nseg);
+            const int k = seg * TILE_M + e.row;
+            const int kc = k < prm.R2 ? k : prm.R2 - 1;
+            const int i = prm.plane_lo + (int)(col / prm.R1), j = (int)(col % prm.R1);
+            const Projected pr = project_point(io, (float)io.axis[0][i], (float)io.axis[1][j], (float)io.axis[2][kc]);
+            e.zf = pr.zf;
+            float pred_lr = 0.0f;
+            const uint32_t cvb = it & 1u;
+            ptx::mbar_wait(&bars->cv_full[cvb], (it >> 1) & 1u, 11, prof);
+            const float *cv = cv_s + cvb * CV_FLOATS;
+#pragma unroll 1
+            for (int m = 0; m < 2; ++m) {
+                const float *cvm = cv + m * CV_STRIDE, *gvm = gv_s + m * GV_STRIDE;
+                e.pred = pred_lr;
+                // layer 0 on the CUDA cores: 16 K blocks of y0 = leaky(C0 + w_z z (+ w_p pred_lr))
+#pragma unroll 1
+                for (int kb = 0; kb < 16; ++kb) {
+                    const uint32_t slot = ring_acquire(e);
+                    const int c = kb * 64 + e.hsel * 32;
+                    const uint32_t dst = a_smem + slot * A_BLK_BYTES;
+                    if (m == 0) finish32<false, true, false>(nullptr, cvm + CV_C0 + c, gvm + GV_WZ0 + c, nullptr, e.zf, 0.f, dst, e.row, e.hsel);
+                    else finish32<false, true, true>(nullptr, cvm + CV_C0 + c, gvm + GV_WZ0 + c, gvm + GV_WP0 + c, e.zf, e.pred, dst, e.row, e.hsel);
+                    ring_publish(e, slot);
+                }
+                // E1: layer 1, both halves (bias b1) -> A ring
+                ptx::mbar_wait(&bars->acc_full[0], acc0 & 1u, 20, prof);
+                ptx::tc_fence_after();
+                epilogue_256<false, false>(e, lane_t0, 0, gvm + GV_B1, nullptr, nullptr);
+                ++acc0;
+                ptx::mbar_wait(&bars->acc_full[1], acc1 & 1u, 21, prof);
+                ptx::tc_fence_after();
+                epilogue_256<false, false>(e, lane_t1, 1, gvm + GV_B1 + 256, nullptr, nullptr);
+                ++acc1;
+                // E2: layer 2 + skip terms -> A ring
+                ptx::mbar_wait(&bars->acc_full[0], acc0 & 1u, 22, prof);
+                ptx::tc_fence_after();
+                if (m == 0) epilogue_256<true, false>(e, lane_t0, 0, cvm + CV_C2, gvm + GV_WZ2, nullptr);
+                else epilogue_256<true, true>(e, lane_t0, 0, cvm + CV_C2, gvm + GV_WZ2, gvm + GV_WP2);
+                ++acc0;
+                // E3: layer 3 + skip terms, layer 4, sigmoid (warps 0-3)
+                ptx::mbar_wait(&bars->acc_full[1], acc1 & 1u, 23, prof);
+                ptx::tc_fence_after();
+                float logit = 0.0f;
+                if (e.hsel == 0) {
+                    logit = cvm[CV_C4] + gvm[GV_WZ4] * e.zf + (m == 1 ? gvm[GV_WP4] * e.pred : 0.0f);
+#pragma unroll 1
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t r[32];
+                        ptx::tmem_ld32(lane_t1 + q * 32, r);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const int c = q * 32 + jj;
+                            float v = __uint_as_float(r[jj]) + cvm[CV_C3 + c] + gvm[GV_WZ3 + c] * e.zf;
+                            if (m == 1) v = fmaf(gvm[GV_WP3 + c], e.pred, v);
+                            logit = fmaf(gvm[GV_W4Y + c], leaky(v), logit);
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bars->acc_free[1]);
+                ++acc1;
+                if (e.hsel == 0) {
+                    const float pred = pr.mask * (1.0f / (1.0f + expf(-logit)));
+                    if (m == 0) {
+                        pred_lr = pred;
+                        pred_x[e.row] = pred;
+                    } else if (k < prm.R2) {
+                        const int64_t n = col * prm.R2 + k;
+                        io.out_hr[n] = pred;
+                        io.out_lr[n] = pred_lr;
+                    }
+                }
+                // the HR pass of rows 32q.. in warp q + 4 needs the pred_lr computed by warp q
+                if (m == 0) {
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+                    if (e.hsel == 1) pred_lr = pred_x[e.row];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars->cv_empty[cvb]);
+        }
+    } else if (warp == NEPI) {
+        // =============================== MMA issue ========================================
+        if (lane == 0) {
+            constexpr uint32_t IDESC256 = ptx::umma_idesc_f16(128, 256);
+            constexpr uint32_t IDESC128 = ptx::umma_idesc_f16(128, 128);
+            uint32_t wblk = 0, ablk = 0, acc0 = 0, acc1 = 0;
+            auto wait_w = [&]() -> uint32_t {
+                const uint32_t s = wblk % NSTAGE;
+                ptx::mbar_wait(&bars->full_w[s], (wblk / NSTAGE) & 1u, 30, prof);
+                ptx::tc_fence_after();
+                return w_smem + s * W_BLK_BYTES;
+            };
+            auto release_w = [&]() {
+                ptx::umma_commit(&bars->empty_w[wblk % NSTAGE]);
+                ++wblk;
+            };
+            auto wait_a = [&]() -> uint32_t {
+                const uint32_t slot = ablk % NA_SLOT;
+                ptx::mbar_wait(&bars->a_ready[slot], (ablk / NA_SLOT) & 1u, 31, prof);
+                ptx::tc_fence_after();
+                return slot;
+            };
+            auto release_a = [&](uint32_t slot) {
+                ptx::umma_commit(&bars->a_free[slot]);
+                ++ablk;
+            };
+            for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+                for (int m = 0; m < 2; ++m) {
+                    // layer 1: K = 1024 (16 blocks), N = 512 -> T0 | T1
+                    ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 33, prof);
+                    ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 34, prof);
+                    ptx::tc_fence_after();
+                    for (int kb = 0; kb < 16; ++kb) {
+                        const uint32_t slot = wait_a();
+                        uint32_t w = wait_w();
+                        mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
+                        release_w();
+                        w = wait_w();
+                        mma_block(T1, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
+                        release_w();
+                        release_a(slot);
+                    }
+                    ptx::umma_commit(&bars->acc_full[0]);
+                    ptx::umma_commit(&bars->acc_full[1]);
+                    ++acc0; ++acc1;
+                    // layer 2: K = 512 (y1 halves from E1), N = 256 -> T0
+                    ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 35, prof);
+                    ptx::tc_fence_after();
+                    for (int kb = 0; kb < 8; ++kb) {
+                        const uint32_t slot = wait_a();
+                        const uint32_t w = wait_w();
+                        mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
+                        release_w();
+                        release_a(slot);
+                    }
+                    ptx::umma_commit(&bars->acc_full[0]);
+                    ++acc0;
+                    // layer 3: K = 256, N = 128 -> T1
+                    ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 36, prof);
+                    ptx::tc_fence_after();
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint32_t slot = wait_a();
+                        const uint32_t w = wait_w();
+                        mma_block(T1, a_smem + slot * A_BLK_BYTES, w, 4, IDESC128, kb == 0);
+                        release_w();
+                        release_a(slot);
+                    }
+                    ptx::umma_commit(&bars->acc_full[1]);
+                    ++acc1;
+                }
+            }
+        }
+    } else {
+        // =============================== weight stream + column vectors ====================
+        if (lane == 0) {
+            uint32_t wblk = 0, it = 0;
+            for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++it) {
+                const uint32_t cvb = it & 1u;
+                ptx::mbar_wait(&bars->cv_empty[cvb], ((it >> 1) & 1u) ^ 1u, 41, prof);
+                ptx::mbar_arrive_expect_tx(&bars->cv_full[cvb], CV_BYTES);
+                ptx::tma_load_1d(smem + SMEM_CV + cvb * CV_BYTES, prm.table + (tile / prm.nseg) * CV_FLOATS, CV_BYTES, &bars->cv_full[cvb]);
+                const uint8_t *src = prm.weights;
+                for (int b = 0; b < 2 * BLOCKS_PER_MLP; ++b) {
+                    const uint32_t bytes = (b % BLOCKS_PER_MLP) < 40 ? W_BLK_BYTES : W128_BLK_BYTES;
+                    const uint32_t s = wblk % NSTAGE;
+                    ptx::mbar_wait(&bars->empty_w[s], ((wblk / NSTAGE) & 1u) ^ 1u, 40, prof);
+                    ptx::mbar_arrive_expect_tx(&bars->full_w[s], bytes);
+                    ptx::tma_load_1d(smem + SMEM_W + s * W_BLK_BYTES, src, bytes, &bars->full_w[s]);
+                    src += bytes;
+                    ++wblk;
+                }
+            }
+        }
+    }
+    if (PROF && threadIdx.x == 0) atomicAdd(g_col_prof + 0, (unsigned long long)(clock64() - t_kernel0));
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == NEPI) ptx::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// table kernel: per-column products of the weight matrices with the image features
+// ------------------------------------------------------------------------------------------
+constexpr int TB_NSTAGE = 3;
+constexpr int TB_THREADS = 6 * 32;
+constexpr int TB_SMEM_F = 0;
+constexpr int TB_SMEM_W = 5 * A_BLK_BYTES;
+constexpr int TB_SMEM_BAR = TB_SMEM_W + TB_NSTAGE * W_BLK_BYTES;
+constexpr int TB_SMEM_TOTAL = TB_SMEM_BAR + 256 + 1024;
+constexpr int TB_CHUNKS = 12;                            // per MLP: 4 x layer 0, layer 2, layer 3 (+ layer 4 row)
+constexpr size_t TB_MLP_BYTES = (size_t)25 * W_BLK_BYTES + 5 * (size_t)W3_BLK_BYTES;
+
+struct TbBars {
+    uint64_t full_w[TB_NSTAGE], empty_w[TB_NSTAGE];
+    uint64_t acc_full[2], acc_free[2];
+    uint64_t f_ready;
+    uint32_t tmem_base;
+};
+
+struct TbParams {
+    const uint8_t *weights;        // 2 x TB_MLP_BYTES
+    const float *bias[2][SURS_NUM_LAYERS];
+    FeatMaps fm;
+    float *table;
+    int64_t ncols;
+    int R1, plane_lo;
+};
+
+__global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_constant__ PointIO io, const __grid_constant__ TbParams prm)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (base - raw);
+    const uint32_t f_smem = base + TB_SMEM_F, w_smem = base + TB_SMEM_W;
+    TbBars *bars = reinterpret_cast<TbBars *>(smem + TB_SMEM_BAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TB_NSTAGE; ++s) { ptx::mbar_init(&bars->full_w[s], 1); ptx::mbar_init(&bars->empty_w[s], 1); }
+        for (int t = 0; t < 2; ++t) { ptx::mbar_init(&bars->acc_full[t], 1); ptx::mbar_init(&bars->acc_free[t], 4); }
+        ptx::mbar_init(&bars->f_ready, 4);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 4) ptx::tmem_alloc(&bars->tmem_base, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    const int64_t ntiles = (prm.ncols + TILE_M - 1) / TILE_M;
+
+    if (warp < 4) {
+        const int row = warp * 32 + lane;
+        uint32_t acc[2] = {0, 0};
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int64_t col = tile * TILE_M + row;
+            const bool valid = col < prm.ncols;
+            if (!valid) col = prm.ncols - 1;
+            const int i = prm.plane_lo + (int)(col / prm.R1), j = (int)(col % prm.R1);
+            const Projected pr = project_point(io, (float)io.axis[0][i], (float)io.axis[1][j], (float)io.axis[2][0]);
+            gather_rows<32>(prm.fm, pr, warp * 32, lane, f_smem);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars->f_ready);
+            float *dst_col = prm.table + col * CV_FLOATS;
+#pragma unroll 1
+            for (int ch = 0; ch < TB_CHUNKS; ++ch) {
+                const int m = ch / 6, cc = ch % 6, t = ch & 1;
+                ptx::mbar_wait(&bars->acc_full[t], acc[t] & 1u, 70);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem + t * 256 + ((uint32_t)(warp * 32) << 16);
+                const int ncols_out = cc < 5 ? 256 : 128;
+                const float *bias = cc < 4 ? prm.bias[m][0] + cc * 256 : (cc == 4 ? prm.bias[m][2] : prm.bias[m][3]);
+                float *dst = dst_col + m * CV_STRIDE + (cc < 4 ? CV_C0 + cc * 256 : (cc == 4 ? CV_C2 : CV_C3));
+#pragma unroll 1
+                for (int c0 = 0; c0 < ncols_out; c0 += 32) {
+                    uint32_t r[32];
+                    ptx::tmem_ld32(taddr + c0, r);
+                    ptx::tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + c0 + 4 * q));
+                            *reinterpret_cast<float4 *>(dst + c0 + 4 * q) =
+                                make_float4(__uint_as_float(r[4 * q]) + b.x, __uint_as_float(r[4 * q + 1]) + b.y,
+                                            __uint_as_float(r[4 * q + 2]) + b.z, __uint_as_float(r[4 * q + 3]) + b.w);
+                        }
+                    }
+                }
+                if (cc == 5) {                                     // column 128 = W4's skip part . f
+                    uint32_t r[32];
+                    ptx::tmem_ld32(taddr + 128, r);
+                    ptx::tmem_ld_wait();
+                    if (valid) dst_col[m * CV_STRIDE + CV_C4] = __uint_as_float(r[0]) + __ldg(prm.bias[m][4]);
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bars->acc_free[t]);
+                ++acc[t];
+            }
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC256 = ptx::umma_idesc_f16(128, 256);
+            constexpr uint32_t IDESC144 = ptx::umma_idesc_f16(128, W3_ROWS);
+            uint32_t wblk = 0, acc[2] = {0, 0}, fcnt = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                ptx::mbar_wait(&bars->f_ready, fcnt & 1u, 71);
+                ++fcnt;
+                ptx::tc_fence_after();
+                for (int ch = 0; ch < TB_CHUNKS; ++ch) {
+                    const int t = ch & 1;
+                    ptx::mbar_wait(&bars->acc_free[t], (acc[t] & 1u) ^ 1u, 72);
+                    ptx::tc_fence_after();
+                    for (int kb = 0; kb < 5; ++kb) {
+                        const uint32_t s = wblk % TB_NSTAGE;
+                        ptx::mbar_wait(&bars->full_w[s], (wblk / TB_NSTAGE) & 1u, 73);
+                        ptx::tc_fence_after();
+                        mma_block(tmem + t * 256, f_smem + kb * A_BLK_BYTES, w_smem + s * W_BLK_BYTES, 4,
+                                  (ch % 6) == 5 ? IDESC144 : IDESC256, kb == 0);
+                        ptx::umma_commit(&bars->empty_w[s]);
+                        ++wblk;
+                    }
+                    ptx::umma_commit(&bars->acc_full[t]);
+                    ++acc[t];
+                }
+            }
+        }
+    } else {
+        if (lane == 0) {
+            uint32_t wblk = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const uint8_t *src = prm.weights;
+                for (int ch = 0; ch < TB_CHUNKS; ++ch)
+                    for (int kb = 0; kb < 5; ++kb) {
+                        const uint32_t bytes = (ch % 6) == 5 ? W3_BLK_BYTES : W_BLK_BYTES;
+                        const uint32_t s = wblk % TB_NSTAGE;
+                        ptx::mbar_wait(&bars->empty_w[s], ((wblk / TB_NSTAGE) & 1u) ^ 1u, 74);
+                        ptx::mbar_arrive_expect_tx(&bars->full_w[s], bytes);
+                        ptx::tma_load_1d(smem + TB_SMEM_W + s * W_BLK_BYTES, src, bytes, &bars->full_w[s]);
+                        src += bytes;
+                        ++wblk;
+                    }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) ptx::tmem_dealloc(tmem, 512);
+}
+
+// per-MLP constant vectors from the fp32 weights
+struct GvSrc {
+    const float *w[SURS_NUM_LAYERS];
+    const float *b1;
+    int cin[SURS_NUM_LAYERS];
+    int has_pred;
+};
+__global__ void build_gv_kernel(GvSrc s0, GvSrc s1, float *gv)
+{
+    const GvSrc &s = blockIdx.x == 0 ? s0 : s1;
+    float *o = gv + blockIdx.x * GV_STRIDE;
+    for (int c = threadIdx.x; c < 1024; c += blockDim.x) {
+        o[GV_WZ0 + c] = s.w[0][(size_t)c * s.cin[0] + 320];
+        o[GV_WP0 + c] = s.has_pred ? s.w[0][(size_t)c * s.cin[0] + 321] : 0.0f;
+    }
+    for (int c = threadIdx.x; c < 512; c += blockDim.x) o[GV_B1 + c] = s.b1[c];
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+        o[GV_WZ2 + c] = s.w[2][(size_t)c * s.cin[2] + 512 + 320];
+        o[GV_WP2 + c] = s.has_pred ? s.w[2][(size_t)c * s.cin[2] + 512 + 321] : 0.0f;
+    }
+    for (int c = threadIdx.x; c < 128; c += blockDim.x) {
+        o[GV_WZ3 + c] = s.w[3][(size_t)c * s.cin[3] + 256 + 320];
+        o[GV_WP3 + c] = s.has_pred ? s.w[3][(size_t)c * s.cin[3] + 256 + 321] : 0.0f;
+        o[GV_W4Y + c] = s.w[4][c];
+    }
+    if (threadIdx.x == 0) {
+        o[GV_WZ4] = s.w[4][128 + 320];
+        o[GV_WP4] = s.has_pred ? s.w[4][128 + 321] : 0.0f;
+        o[GV_WP4 + 1] = 0.0f;
+        o[GV_WP4 + 2] = 0.0f;
+    }
+}
+
+}  // namespace
+
+int surs_col_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS], cudaStream_t st)
+{
+    const size_t total = 2 * MLP_BYTES + 2 * TB_MLP_BYTES + GV_BYTES;
+    if (!ctx->col_weights) SURS_CUDA(ctx, cudaMalloc(&ctx->col_weights, total));
+    uint8_t *base = (uint8_t *)ctx->col_weights;
+    PackDesc host[2 * BLOCKS_PER_MLP + 2 * 30];
+    int n = 0;
+    uint32_t off = 0;
+    auto add = [&](int m, int layer, int row0, int nrows, int ntotal, int fblock, int k0, bool extra) {
+        PackDesc d;
+        memset(&d, 0, sizeof(d));
+        d.w = w[m][layer];
+        d.cin = ctx->cin[m][layer];
+        d.w_extra = extra ? w[m][4] : nullptr;
+        d.k0_extra = 128;
+        d.row0 = row0; d.nrows = nrows; d.ntotal = ntotal; d.fblock = fblock; d.k0 = k0;
+        d.c0 = m == 0 ? SURS_C0_LR : SURS_C0_HR;
+        d.out_off = off;
+        off += (uint32_t)ntotal * 128u;
+        host[n++] = d;
+    };
+    for (int m = 0; m < 2; ++m) {                                   // main stream
+        for (int kb = 0; kb < 16; ++kb) {
+            add(m, 1, 0, 256, 256, -1, kb * 64, false);
+            add(m, 1, 256, 256, 256, -1, kb * 64, false);
+        }
+        for (int kb = 0; kb < 8; ++kb) add(m, 2, 0, 256, 256, -1, kb * 64, false);
+        for (int kb = 0; kb < 4; ++kb) add(m, 3, 0, 128, 128, -1, kb * 64, false);
+    }
+    if (off != 2 * MLP_BYTES) SURS_FAIL(ctx, "internal: column weight stream size mismatch");
+    for (int m = 0; m < 2; ++m) {                                   // table stream (image-feature columns only)
+        for (int c = 0; c < 4; ++c)
+            for (int kb = 0; kb < 5; ++kb) add(m, 0, c * 256, 256, 256, kb, 0, false);
+        for (int kb = 0; kb < 5; ++kb) add(m, 2, 0, 256, 256, kb, 512, false);
+        for (int kb = 0; kb < 5; ++kb) add(m, 3, 0, 128, W3_ROWS, kb, 256, true);
+    }
+    if (off != 2 * MLP_BYTES + 2 * TB_MLP_BYTES) SURS_FAIL(ctx, "internal: table weight stream size mismatch");
+    PackDesc *dev = nullptr;
+    SURS_CUDA(ctx, cudaMalloc(&dev, sizeof(PackDesc) * n));
+    SURS_CUDA(ctx, cudaMemcpyAsync(dev, host, sizeof(PackDesc) * n, cudaMemcpyHostToDevice, st));
+    pack_weights_kernel<<<n, 256, 0, st>>>(dev, base);
+    SURS_LAUNCH_CHECK(ctx, "pack_weights_kernel(col)");
+    GvSrc s[2];
+    for (int m = 0; m < 2; ++m) {
+        for (int l = 0; l < SURS_NUM_LAYERS; ++l) { s[m].w[l] = w[m][l]; s[m].cin[l] = ctx->cin[m][l]; }
+        s[m].b1 = ctx->b32[m][1];
+        s[m].has_pred = m;
+    }
+    build_gv_kernel<<<2, 256, 0, st>>>(s[0], s[1], reinterpret_cast<float *>(base + 2 * MLP_BYTES + 2 * TB_MLP_BYTES));
+    SURS_LAUNCH_CHECK(ctx, "build_gv_kernel");
+    SURS_CUDA(ctx, cudaStreamSynchronize(st));
+    SURS_CUDA(ctx, cudaFree(dev));
+    return 0;
+}
+
+// Dense slab evaluation through the column-factored kernels.  io: grid mode, lin_base / n / out_* set
+// for planes [plane_lo, plane_lo + nplanes) of a [R0, R1, R2] grid without transform.
+int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st)
+{
+    const int64_t ncols = (int64_t)nplanes * R1;
+    if (ncols <= 0) return 0;
+    if (surs_ensure(ctx, (void **)&ctx->col_table, &ctx->col_table_cap, (size_t)ncols * CV_BYTES)) return 1;
+    uint8_t *base = (uint8_t *)ctx->col_weights;
+    TbParams tb;
+    tb.weights = base + 2 * MLP_BYTES;
+    for (int m = 0; m < 2; ++m)
+        for (int l = 0; l < SURS_NUM_LAYERS; ++l) tb.bias[m][l] = ctx->b32[m][l];
+    tb.fm.f_lr = ctx->f_lr16; tb.fm.f_hr = ctx->f_hr16;
+    tb.fm.H_lr = ctx->H_lr; tb.fm.W_lr = ctx->W_lr; tb.fm.H_hr = ctx->H_hr; tb.fm.W_hr = ctx->W_hr;
+    tb.table = (float *)ctx->col_table;
+    tb.ncols = ncols; tb.R1 = R1; tb.plane_lo = plane_lo;
+    const int64_t tb_tiles = (ncols + TILE_M - 1) / TILE_M;
+    const int tb_grid = (int)(tb_tiles < ctx->sm_count ? tb_tiles : ctx->sm_count);
+    SURS_CUDA(ctx, cudaFuncSetAttribute(col_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
+    col_table_kernel<<<tb_grid, TB_THREADS, TB_SMEM_TOTAL, st>>>(io, tb);
+    SURS_LAUNCH_CHECK(ctx, "col_table_kernel");
+
+    ColParams prm;
+    prm.weights = base;
+    prm.gv = reinterpret_cast<const float *>(base + 2 * MLP_BYTES + 2 * TB_MLP_BYTES);
+    prm.table = (const float *)ctx->col_table;
+    prm.nseg = (R2 + TILE_M - 1) / TILE_M;
+    prm.ntiles = ncols * prm.nseg;
+    prm.R1 = R1; prm.R2 = R2; prm.plane_lo = plane_lo;
+    const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
+    static const bool profile = getenv("SURS_TC_PROFILE") != nullptr;
+    if (!profile) {
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        query_col_kernel<false><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+        SURS_LAUNCH_CHECK(ctx, "query_col_kernel");
+        return 0;
+    }
+    unsigned long long zero[64] = {0}, h[64];
+    SURS_CUDA(ctx, cudaMemcpyToSymbol(g_col_prof, zero, sizeof(zero)));
+    SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    query_col_kernel<true><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+    SURS_LAUNCH_CHECK(ctx, "query_col_kernel<profile>");
+    SURS_CUDA(ctx, cudaStreamSynchronize(st));
+    SURS_CUDA(ctx, cudaMemcpyFromSymbol(h, g_col_prof, sizeof(h)));
+    const double k = 1e-3 / (double)prm.ntiles;
+    fprintf(stderr, "[surs col profile] tiles=%lld grid=%d kcycles/tile: total %.1f | epi warp0: wait_cv %.1f wait_a_free %.1f wait_acc_full(E1a %.1f E1b %.1f E2 %.1f E3 %.1f) "
+                    "| mma: wait_w %.1f wait_a_ready %.1f wait_acc_free(%.1f %.1f %.1f %.1f) | loader wait_empty %.1f wait_cv_empty %.1f\n",
+            (long long)prm.ntiles, grid, h[0] * k, h[11] * k, h[10] * k, h[20] * k, h[21] * k, h[22] * k, h[23] * k,
+            h[30] * k, h[31] * k, h[33] * k, h[34] * k, h[35] * k, h[36] * k, h[40] * k, h[41] * k);
+    return 0;
+}

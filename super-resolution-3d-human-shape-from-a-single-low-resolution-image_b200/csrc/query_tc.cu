@@ -23,18 +23,14 @@
 // 8 = MMA issue (one elected lane), 9 = weight stream (cp.async.bulk of pre-swizzled 32 KB
 // blocks laid out in HBM in consumption order, 3-stage ring), 10 = scratch reload.
 // All hand-offs are mbarriers; waits are bounded (a protocol bug traps instead of hanging).
-#include "common.cuh"
-#include "ptx.cuh"
+#include "tc_common.cuh"
 
 #include <stdlib.h>
 
 namespace {
 
-constexpr int TILE_M = 128;
-constexpr int A_BLK_BYTES = TILE_M * 128;      // 16 KB: 128 rows x 64 fp16
-constexpr int W_BLK_BYTES = 256 * 128;         // 32 KB: 256 rows x 64 fp16
-constexpr int W3_ROWS = 144;                   // layer 3: 128 outputs + W4's skip row + padding to 16
-constexpr int W3_BLK_BYTES = W3_ROWS * 128;
+using namespace tc;
+
 constexpr int NF_BLK = 6;                      // F tile: 4 (lr) + 1 (hr) + 1 tail (z, pred_lr, ones)
 constexpr int NA_SLOT = 2;                     // ring of A-operand K blocks (activations)
 constexpr int NSTAGE = 3;                      // weight ring
@@ -61,42 +57,11 @@ struct Bars {
 
 struct TcParams {
     const uint8_t *weights;                    // 2 x MLP_BYTES
-    const __half *f_lr, *f_hr;
-    int H_lr, W_lr, H_hr, W_hr;
+    FeatMaps fm;
     uint8_t *scratch;                          // 64 KB per CTA
     int64_t ntiles;
     float w4y[2][128];                         // W4[0, 0:128] of both MLPs (fp32, used in the last epilogue)
 };
-
-// byte offset of 16-byte chunk `chunk` of row `row` inside a [rows x 64] fp16 SWIZZLE_128B block
-__host__ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk)
-{
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
-}
-
-__device__ __forceinline__ uint32_t pack_h2(float a, float b)
-{
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&h);
-}
-
-__device__ __forceinline__ float leaky(float v) { return fmaxf(v, SURS_LEAKY * v); }
-
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v)
-{
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-__device__ __forceinline__ void accum_tap(float (&acc)[8], uint4 v, float w)
-{
-    const __half2 *h = reinterpret_cast<const __half2 *>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float2 f = __half22float2(h[i]);
-        acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
-        acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
-    }
-}
 
 __device__ __forceinline__ Projected project_row(const PointIO &io, int64_t tile, int row)
 {
@@ -105,48 +70,6 @@ __device__ __forceinline__ Projected project_row(const PointIO &io, int64_t tile
     float x, y, z;
     pointio_load(io, n, x, y, z);
     return project_point(io, x, y, z);
-}
-
-// ---- gather: warp w fills rows 32*(w%4) + 16*(w/4) .. +15 of the F tile -----------------------
-__device__ __forceinline__ void gather_rows(const PointIO &io, const TcParams &prm, int64_t tile, int warp, int lane, uint32_t f_smem)
-{
-    const int row0 = (warp & 3) * 32 + (warp >> 2) * 16;
-    const Projected pr = project_row(io, tile, row0 + (lane & 15));      // lanes 16-31 mirror lanes 0-15
-    const Taps tl = make_taps(pr.u, pr.v, prm.H_lr, prm.W_lr);
-    const Taps th = make_taps(pr.u, pr.v, prm.H_hr, prm.W_hr);
-    // low-res map: 256 channels = 32 lanes x 8 channels, one point per step
-#pragma unroll 8
-    for (int p = 0; p < 16; ++p) {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int off = __shfl_sync(0xffffffffu, tl.off[q], p);
-            const float w = __shfl_sync(0xffffffffu, tl.w[q], p);
-            if (off >= 0) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(prm.f_lr + (size_t)off * SURS_C_LR) + lane);
-                accum_tap(acc, v, w);
-            }
-        }
-        const uint4 o = make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7]));
-        st_shared_v4(f_smem + (lane >> 3) * A_BLK_BYTES + sw128_off(row0 + p, lane & 7), o);
-    }
-    // high-res map: 64 channels = 8 lanes x 8 channels, four points per step
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int p = it * 4 + (lane >> 3);
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int off = __shfl_sync(0xffffffffu, th.off[q], p);
-            const float w = __shfl_sync(0xffffffffu, th.w[q], p);
-            if (off >= 0) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(prm.f_hr + (size_t)off * SURS_C_HR) + (lane & 7));
-                accum_tap(acc, v, w);
-            }
-        }
-        const uint4 o = make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7]));
-        st_shared_v4(f_smem + 4 * A_BLK_BYTES + sw128_off(row0 + p, lane & 7), o);
-    }
 }
 
 // tail block columns: [z_hi, z_lo, pred_hi, pred_lo, 1, 1, 0, 0 | 0 x 8]; the hi/lo splits keep
@@ -192,15 +115,6 @@ __device__ __forceinline__ void epilogue_256(uint32_t taddr, int row, int hsel, 
             if (lane == 0) ptx::mbar_arrive(&bars->a_ready[slot]);
         }
     }
-}
-
-// K-major MMAs over one 64-wide (or 16-wide tail) K block
-__device__ __forceinline__ void mma_block(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int ksteps, uint32_t idesc, bool zero_first)
-{
-    const uint64_t da = ptx::umma_desc_sw128(a_addr), db = ptx::umma_desc_sw128(w_addr);
-#pragma unroll 1
-    for (int k = 0; k < ksteps; ++k)
-        ptx::umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (zero_first && k == 0) ? 0u : 1u);
 }
 
 __device__ unsigned long long g_tc_prof[64];
@@ -249,7 +163,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_tc_kernel(const __grid_cons
         };
         for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
             const long long t_g0 = PROF ? clock64() : 0;
-            gather_rows(io, prm, tile, warp, lane, f_smem);
+            {   // warp w fills rows 32 (w % 4) + 16 (w / 4) .. + 15; lanes 16-31 mirror lanes 0-15
+                const int row0 = (warp & 3) * 32 + (warp >> 2) * 16;
+                gather_rows<16>(prm.fm, project_row(io, tile, row0 + (lane & 15)), row0, lane, f_smem);
+            }
             float zf = 0.f, mask = 0.f;
             if (hsel == 0) {                       // warps 0-3 own the per-row scalars and the tail block
                 const Projected own = project_row(io, tile, row);
@@ -465,72 +382,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_tc_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------
-// weight packing: fp32 [Cout, Cin] (+ bias) -> the block stream consumed above
-// ------------------------------------------------------------------------------------------
-struct PackDesc {
-    const float *w;        // source layer, row-major [cout][cin]
-    const float *w_extra;  // layer 4 (row 128 of the layer-3 skip blocks) or NULL
-    const float *bias;     // bias of the rows (tail blocks only) or NULL
-    const float *bias_extra;
-    int cin;
-    int row0, nrows;       // rows taken from w; the block has ntotal rows, the rest is zero
-    int ntotal;
-    int fblock;            // -1: plain columns k0 .. k0+63; else F-order block index 0..5
-    int bias_only;         // tail block that carries nothing but the bias (layer 1)
-    int k0, k0_extra;      // first column (plain) / start of the skip part (F-order)
-    int c0;                // 321 / 322: width of the skip input
-    uint32_t out_off;
-};
-
-// column of the skip input that F-tile position (fblock, kk) holds; -1 padding, -2 / -3 bias hi / lo
-__device__ __forceinline__ int fmap(int fblock, int kk, int c0)
-{
-    if (fblock < 4) return fblock * 64 + kk;
-    if (fblock == 4) return 256 + kk;
-    if (kk < 2) return 320;                      // z_hi, z_lo
-    if (kk < 4) return c0 > 321 ? 321 : -1;      // pred_hi, pred_lo (HR MLP only)
-    if (kk == 4) return -2;
-    if (kk == 5) return -3;
-    return -1;
-}
-
-__global__ void pack_weights_kernel(const PackDesc *descs, uint8_t *out)
-{
-    const PackDesc d = descs[blockIdx.x];
-    for (int ch = threadIdx.x; ch < d.ntotal * 8; ch += blockDim.x) {
-        const int r = ch >> 3, c = ch & 7;
-        uint32_t packed[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float v[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int kk = c * 8 + 2 * i + j;
-                float x = 0.0f;
-                if (d.fblock < 0) {
-                    if (r < d.nrows) x = d.w[(size_t)(d.row0 + r) * d.cin + d.k0 + kk];
-                } else {
-                    const int col = fmap(d.fblock, kk, d.c0);
-                    if (col >= 0 && !d.bias_only) {
-                        if (r < d.nrows) x = d.w[(size_t)(d.row0 + r) * d.cin + d.k0 + col];
-                        else if (r == 128 && d.w_extra) x = d.w_extra[d.k0_extra + col];
-                    } else if (col <= -2) {
-                        float b = 0.0f;
-                        if (r < d.nrows && d.bias) b = d.bias[d.row0 + r];
-                        else if (r == 128 && d.bias_extra) b = d.bias_extra[0];
-                        const float hi = __half2float(__float2half_rn(b));
-                        x = col == -2 ? hi : b - hi;
-                    }
-                }
-                v[j] = x;
-            }
-            packed[i] = pack_h2(v[0], v[1]);
-        }
-        *reinterpret_cast<uint4 *>(out + d.out_off + sw128_off(r, c)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // self test: D[128,N] = A[128,K] . B[N,K]^T through the same descriptors / layouts
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float *A, const float *B, int N, int K, int tail16, float *D)
@@ -653,8 +504,8 @@ int surs_launch_query_tc(surs_ctx *ctx, const PointIO &io, cudaStream_t st)
     TcParams prm;
     prm.weights = (const uint8_t *)ctx->tc_weights;
     memcpy(prm.w4y, ctx->tc_w4y, sizeof(prm.w4y));
-    prm.f_lr = ctx->f_lr16; prm.f_hr = ctx->f_hr16;
-    prm.H_lr = ctx->H_lr; prm.W_lr = ctx->W_lr; prm.H_hr = ctx->H_hr; prm.W_hr = ctx->W_hr;
+    prm.fm.f_lr = ctx->f_lr16; prm.fm.f_hr = ctx->f_hr16;
+    prm.fm.H_lr = ctx->H_lr; prm.fm.W_lr = ctx->W_lr; prm.fm.H_hr = ctx->H_hr; prm.fm.W_hr = ctx->W_hr;
     prm.ntiles = (io.n + TILE_M - 1) / TILE_M;
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
     if (surs_ensure(ctx, (void **)&ctx->tc_scratch, &ctx->tc_scratch_cap, (size_t)ctx->sm_count * 4 * A_BLK_BYTES)) return 1;

@@ -64,6 +64,8 @@ extern "C" void surs_destroy(surs_ctx *ctx)
         }
     cudaFree(ctx->tc_weights);
     cudaFree(ctx->tc_scratch);
+    cudaFree(ctx->col_weights);
+    cudaFree(ctx->col_table);
     cudaFree(ctx->f_lr32); cudaFree(ctx->f_hr32); cudaFree(ctx->f_lr16); cudaFree(ctx->f_hr16);
     cudaFree(ctx->axis_dev); cudaFree(ctx->dirty); cudaFree(ctx->idx_list); cudaFree(ctx->counter);
     cudaFree(ctx->stage_pts); cudaFree(ctx->stage_out);
@@ -126,6 +128,7 @@ extern "C" int surs_set_weights(surs_ctx *ctx,
         }
     }
     if (surs_tc_pack_weights(ctx, wsrc, st)) return 1;
+    if (surs_col_pack_weights(ctx, wsrc, st)) return 1;
     SURS_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->have_weights = 1;
     return 0;
@@ -295,6 +298,10 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
     // outputs are slab-relative: out[n]
     io.out_hr = sdf_hr;
     io.out_lr = sdf_lr;
+    // column-factored path: (u,v) must not depend on the grid's last axis (see query_col.cu)
+    static const bool no_column = getenv("SURS_NO_COLUMN") != nullptr;
+    if (precision == SURS_PREC_FP16 && !transform && calib[2] == 0.0f && calib[6] == 0.0f && res[2] >= 64 && !no_column)
+        return surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st);
     // one launch handles < 2^31 CTAs; split very large slabs
     const int64_t chunk = (int64_t)1 << 30;
     for (int64_t s = 0; s < io.n; s += chunk) {

@@ -235,3 +235,26 @@ def test_marching_cubes_slabs_reproduce_single_volume(ctx):
 def test_marching_cubes_no_surface_gives_zero_counts(ctx):
     vol = torch.zeros((8, 8, 8), device=ctx.device)
     assert ctx.mc_count(vol, 0.5)[:2] == (0, 0)
+
+
+def test_column_factored_dense_path(ctx, case32):
+    """surs_eval_grid takes the column-factored kernels (query_col.cu) when (u,v) do not depend on
+    the last grid axis; same occupancies as the fp32 mode / the generic tensor-core kernel."""
+    from surs_b200 import _capi
+    for res, bmax in (((64, 64, 64), [0.5, 0.5, 0.5]), ((5, 9, 200), [0.5, 0.4, 0.55]), ((3, 130, 128), [0.2, 0.5, 0.5])):
+        args = (res, [-0.5] * 3, bmax, case32.calib) + znum(case32)
+        col = ctx.eval_grid(*args, precision=_capi.PREC_FP16)
+        ref = ctx.eval_grid(*args, precision=_capi.PREC_FP32)
+        coords, _ = O.create_grid(*res, np.array([-0.5] * 3), np.array(bmax))
+        pts = torch.from_numpy(coords.reshape(3, -1).astype(np.float32)).to(ctx.device)
+        gen = ctx.query(pts, case32.calib, *znum(case32), precision=_capi.PREC_FP16)
+        for a, b, g in zip(col, ref, gen):
+            d = (a - b).abs()
+            print("column path %s: max|d| vs fp32 %.3g mean %.3g; vs generic tc %.3g" %
+                  (res, d.max().item(), d.mean().item(), (a.reshape(-1) - g).abs().max().item()))
+            assert d.max().item() < TOL_FP16_MAX and d.mean().item() < TOL_FP16_MEAN
+            assert np.array_equal((a == 0).cpu().numpy(), (b == 0).cpu().numpy())
+        # a slab of the same grid is bit identical to the corresponding planes
+        if res[0] >= 5:
+            slab = ctx.eval_grid(*args, precision=_capi.PREC_FP16, plane_lo=1, plane_hi=4)
+            assert torch.equal(col[0][1:4], slab[0]) and torch.equal(col[1][1:4], slab[1])
