@@ -1,0 +1,175 @@
+"""GPU tests of the drop-in Python layer (surs_b200.lib.*): the reference's call shapes give the
+reference's results.  Run on the B200 box: pytest -m gpu."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import mc_oracle
+from oracle import surs_oracle as O
+from surs_b200 import _capi
+from surs_b200 import synthetic as syn
+from surs_b200.lib import mesh_util, sdf, train_util
+from surs_b200.lib.model import SuRSNet
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class FakeEncoder(torch.nn.Module):
+    """Stands in for SuRSSR_v3 + HGFilter: returns the synthetic feature maps."""
+
+    def __init__(self, case):
+        super().__init__()
+        self.f_lr = torch.from_numpy(case.feat_lr)[None].to(DEV)
+        self.f_hr = torch.from_numpy(case.feat_hr)[None].to(DEV)
+
+    def super_res(self, images):
+        return images, self.f_lr, self.f_hr
+
+    def filter_lr(self, x):
+        return [x * 0.5, x * 0.7, x]          # three hourglass outputs; eval mode keeps the last
+
+    def filter_hr(self, x):
+        return [x]
+
+
+def make_net(case, precision=_capi.PREC_FP16, encoder=None):
+    opt = helpers.make_opt(loadSize=case.load_size, z_size=case.z_size)
+    net = SuRSNet(opt, precision=precision, encoder=encoder).to(DEV).eval()
+    sd = {}
+    for name, (ws, bs) in (("mlp_lr", case.mlp_lr), ("mlp_hr", case.mlp_hr)):
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            sd["%s.conv%d.weight" % (name, i)] = torch.from_numpy(w)[:, :, None]
+            sd["%s.conv%d.bias" % (name, i)] = torch.from_numpy(b)
+    missing, unexpected = net.load_state_dict(sd, strict=False)      # reference checkpoint keys for the MLPs
+    assert not unexpected and not [k for k in missing if k.startswith("mlp_")]
+    net.im_feat_list_lr = [torch.from_numpy(case.feat_lr)[None].to(DEV)]
+    net.im_feat_list_hr = [torch.from_numpy(case.feat_hr)[None].to(DEV)]
+    return opt, net
+
+
+@pytest.fixture(scope="module")
+def case32():
+    return syn.SyntheticCase(S=32, seed=0)
+
+
+def test_query_api_matches_reference_semantics(case32, golden_dir):
+    g = np.load(os.path.join(golden_dir, "query_golden.npz"))
+    opt, net = make_net(case32, precision=_capi.PREC_FP32)
+    pts = torch.from_numpy(g["points"])[None].to(DEV)
+    calib = torch.from_numpy(case32.calib)[None].to(DEV)
+    net.query_mr(pts, calib)
+    assert net.preds_lr.shape == (1, 1, pts.shape[2])
+    net.query_sr(pts, calib)
+    hr, lr = net.get_preds()                                       # HR first (BaseSuRSNet.py:85)
+    assert np.abs(hr[0, 0].cpu().numpy() - g["pred_hr"]).max() < 2e-5
+    assert np.abs(lr[0, 0].cpu().numpy() - g["pred_lr"]).max() < 2e-5
+    assert torch.equal(net.query(pts, calib), hr)                  # PIFu alias
+    # the torch path for uncovered variants gives the same numbers (and warns)
+    net.train()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                        # cuDNN's TF32 convs are ~5e-4 off
+    try:
+        with pytest.warns(UserWarning):
+            net.query_mr(pts, calib)
+            net.query_sr(pts, calib)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    net.eval()
+    assert np.abs(net.preds_hr[0, 0].detach().cpu().numpy() - g["pred_hr"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("use_octree,res", [(False, 64), (True, 128)])
+def test_reconstruction_fast_path(case32, use_octree, res):
+    opt, net = make_net(case32)
+    calib = torch.from_numpy(case32.calib)[None].to(DEV)
+    b_min, b_max = np.array([-0.5] * 3), np.array([0.5] * 3)
+    out, stats = mesh_util.reconstruction(opt, net, DEV, calib, res, b_min, b_max, use_octree=use_octree, return_stats=True)
+    assert len(out) == 8
+    ctx = net.surs_context()
+    zn, zd = net.depth_scale()
+    if use_octree:
+        a, b, n_eval = ctx.eval_grid_octree((res,) * 3, b_min, b_max, calib, zn, zd, opt.threshold)
+        vols = (a.float(), b.float())
+        assert stats["n_evaluated"] == n_eval < res ** 3
+    else:
+        vols = ctx.eval_grid((res,) * 3, b_min, b_max, calib, zn, zd)
+    _, mat = O.create_grid(res, res, res, b_min, b_max)
+    for k, vol in enumerate(vols):
+        v, f, n, val = mc_oracle.marching_cubes_lewiner(vol.cpu().numpy(), 0.5)
+        verts, faces, normals, values = out[4 * k:4 * k + 4]
+        assert verts.dtype == np.float64 and faces.dtype == np.int32 and normals.dtype == np.float32
+        assert np.array_equal(faces, f)
+        assert np.allclose(verts, O.verts_to_world(mat, v), rtol=0, atol=1e-12)
+        assert np.array_equal(values, val)
+    # PIFu call shape (no opt) gives the same mesh
+    out2 = mesh_util.reconstruction(net, DEV, calib, res, b_min, b_max, use_octree)
+    assert all(np.array_equal(x, y) for x, y in zip(out, out2))
+
+
+def test_reconstruction_generic_path_with_foreign_net():
+    """Any object with query_mr / query_sr / get_preds works (eval_func closure, lib/mesh_util.py:20-28)."""
+
+    class Foreign:
+        num_views = 1
+
+        def query_mr(self, samples, calib):
+            self.p = samples
+
+        def query_sr(self, samples, calib):
+            pass
+
+        def get_preds(self):
+            hr, lr = helpers.analytic_eval_func(self.p[0].cpu().numpy().astype(np.float64))
+            return torch.from_numpy(hr), torch.from_numpy(lr)
+
+    opt = helpers.make_opt()
+    b_min, b_max = np.array([-0.5] * 3), np.array([0.5] * 3)
+    for use_octree in (False, True):
+        out = mesh_util.reconstruction(opt, Foreign(), DEV, None, 64, b_min, b_max, use_octree=use_octree, num_samples=30000)
+        coords, mat = O.create_grid(64, 64, 64, b_min, b_max)
+        if use_octree:
+            hr, lr = O.eval_grid_octree(opt.threshold, coords, helpers.analytic_eval_func, num_samples=30000)
+        else:
+            hr, lr = O.eval_grid(coords, helpers.analytic_eval_func, num_samples=30000)
+        v, f, _, _ = mc_oracle.marching_cubes_lewiner(hr.astype(np.float32), 0.5)
+        assert np.array_equal(out[1], f) and np.allclose(out[0], O.verts_to_world(mat, v), atol=1e-12)
+        v, f, _, _ = mc_oracle.marching_cubes_lewiner(lr.astype(np.float32), 0.5)
+        assert np.array_equal(out[5], f)
+
+
+def test_sdf_module_matches_oracle():
+    coords, mat = sdf.create_grid(16, 12, 20, np.array([-1.0, 0, 0.5]), np.array([1.0, 2, 1.5]))
+    oc, om = O.create_grid(16, 12, 20, np.array([-1.0, 0, 0.5]), np.array([1.0, 2, 1.5]))
+    assert np.array_equal(coords, oc) and np.array_equal(mat, om)
+    assert np.array_equal(sdf.grid_matrix((16, 12, 20), [-1.0, 0, 0.5], [1.0, 2, 1.5]), om)
+    coords, _ = sdf.create_grid(32, 32, 32, np.array([-0.5] * 3), np.array([0.5] * 3))
+    opt = helpers.make_opt()
+    a = sdf.eval_grid_octree(opt, coords, helpers.analytic_eval_func, init_resolution=8, num_samples=5000)
+    b = O.eval_grid_octree_sequential(0.05, coords, helpers.analytic_eval_func, init_resolution=8, num_samples=5000)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_marching_cubes_errors_mirror_skimage():
+    with pytest.raises(ValueError):
+        mesh_util.marching_cubes_lewiner(np.zeros((8, 8, 8), np.float32), 0.5)
+    v, f, n, val = mesh_util.marching_cubes_lewiner(helpers.sphere_volume(24, 7.2), 0.5)
+    assert helpers.mesh_euler_closed(v, f) == 2
+
+
+def test_gen_mesh_writes_reference_obj(case32, tmp_path):
+    opt, net = make_net(case32, encoder=FakeEncoder(case32))
+    opt.resolution = 64
+    data = {"img_LR": torch.zeros(1, 3, 32, 32), "b_min": np.array([-0.5] * 3), "b_max": np.array([0.5] * 3)}
+    path = str(tmp_path / "subject.obj")
+    train_util.gen_mesh(opt, net, DEV, data, path, use_octree=False)
+    calib = train_util.make_calib(DEV)
+    out = mesh_util.reconstruction(opt, net, DEV, calib, 64, data["b_min"], data["b_max"], use_octree=False)
+    with open(path[:-4] + "_HR.obj") as fh:
+        assert fh.read() == O.obj_text(out[0], out[1])
+    with open(path[:-4] + "_LR.obj") as fh:
+        assert fh.read() == O.obj_text(out[4], out[5])
