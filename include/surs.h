@@ -170,6 +170,10 @@ int surs_save_obj_mesh(const char *path, const double *verts, int64_t n_verts,
 int surs_selftest_umma(surs_ctx *ctx, const float *A, const float *B, int N, int K, int tail16,
                        float *D, void *stream);
 
+/* Same for the CTA-pair path (tcgen05.mma.cta_group::2, one cluster of two CTAs):
+ * D[256,N] = A[256,K] . B[N,K]^T, N multiple of 32 in [32,256], K <= 192. */
+int surs_selftest_umma2(surs_ctx *ctx, const float *A, const float *B, int N, int K, float *D, void *stream);
+
 /* Counters for bench.py's "gpu_launches": kernels launched by this context so far. */
 int64_t surs_launch_count(const surs_ctx *ctx);
 

@@ -49,6 +49,7 @@ SIGNATURES = {
     "surs_cast_f64_f32": (ctypes.c_int, [_P, _P, _P, _I64, _P]),
     "surs_save_obj_mesh": (ctypes.c_int, [ctypes.c_char_p, _P, _I64, _P, _I64]),
     "surs_selftest_umma": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P]),
+    "surs_selftest_umma2": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
     "surs_launch_count": (_I64, [_P]),
 }
 
@@ -303,3 +304,13 @@ def save_obj_mesh(mesh_path, verts, faces):
     f = np.ascontiguousarray(np.asarray(faces, dtype=np.int32).reshape(-1, 3))
     if load().surs_save_obj_mesh(os.fsencode(mesh_path), v.ctypes.data, v.shape[0], f.ctypes.data, f.shape[0]):
         raise OSError("could not write %s" % mesh_path)
+
+
+def selftest_umma2(ctx, A, B):
+    """D[256,N] = A[256,K] . B[N,K]^T through tcgen05.mma.cta_group::2 (unit test of the CTA-pair path)."""
+    A = A.to(ctx.device, torch.float32).contiguous()
+    B = B.to(ctx.device, torch.float32).contiguous()
+    D = torch.empty((256, B.shape[0]), device=ctx.device, dtype=torch.float32)
+    with torch.cuda.device(ctx.device):
+        ctx._check(ctx.lib.surs_selftest_umma2(ctx._h, _ptr(A), _ptr(B), B.shape[0], A.shape[1], _ptr(D), _stream(ctx.device)))
+    return D
