@@ -158,7 +158,11 @@ struct surs_ctx {
     float mc_level;
     int mc_flags;
     int64_t mc_nv, mc_nf, mc_id_offset;
-    uint2 *mc_block_tot;                   // per-block (verts, tris), then exclusive prefix
+    int mc_fast;                           // R2 % 4 == 0: quad classification + compact active-cell list
+    int64_t mc_nact;
+    void *mc_cells;                        // active cells in scan order (CellRec, mc.cu)
+    size_t mc_cells_cap;
+    void *mc_block_tot;                    // per-block totals, then exclusive prefix (uint2 / uint4)
     size_t mc_block_cap;
     int32_t *mc_vid;                       // edge -> vertex id map, 3 per node
     size_t mc_vid_cap;

@@ -16,6 +16,7 @@
 #include "mc_tables.h"
 
 #include <float.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -54,15 +55,27 @@ struct Cell {
 
 __device__ __forceinline__ int64_t node_lin(const McParams &p, int i, int j, int k) { return ((int64_t)i * p.R1 + j) * p.R2 + k; }
 
+__device__ __forceinline__ void classify_vals(const McParams &p, int i, int j, int k, const float (&val)[8], Cell &c);
+
 __device__ __forceinline__ void classify(const McParams &p, int i, int j, int k, Cell &c)
 {
     c.entry = -1; c.nv = 0; c.nt = 0; c.owned = 0; c.ambiguous = 0;
     if (i >= p.R0 - 1 || j >= p.R1 - 1 || k >= p.R2 - 1) return;
+    float val[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        val[q] = __ldg(p.vol + node_lin(p, i + c_corner_off[3 * q], j + c_corner_off[3 * q + 1], k + c_corner_off[3 * q + 2]));
+    classify_vals(p, i, j, k, val, c);
+}
+
+// val[q] = volume value at corner q of cell (i,j,k) (which must be a valid cell)
+__device__ __forceinline__ void classify_vals(const McParams &p, int i, int j, int k, const float (&val)[8], Cell &c)
+{
+    c.entry = -1; c.nv = 0; c.nt = 0; c.owned = 0; c.ambiguous = 0;
     unsigned cas = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const float v = __ldg(p.vol + node_lin(p, i + c_corner_off[3 * q], j + c_corner_off[3 * q + 1], k + c_corner_off[3 * q + 2]));
-        c.d[q] = __dsub_rn((double)v, p.level);
+        c.d[q] = __dsub_rn((double)val[q], p.level);
         if (c.d[q] > 0.0) cas |= 1u << q;
     }
     if (cas == 0 || cas == 255) return;
@@ -233,20 +246,9 @@ __device__ __forceinline__ void write_vertex(const McOut &o, int64_t v, const do
     if (o.values) o.values[v] = (float)value;
 }
 
-__global__ void __launch_bounds__(MC_THREADS) mc_emit_verts_kernel(McParams p, int64_t nnode, const uint2 *block_prefix, McOut o)
+// all vertices created by cell (i,j,k); vbase = index of its first vertex in this volume's list
+__device__ __forceinline__ void emit_cell_verts(const McParams &p, const McOut &o, int i, int j, int k, const Cell &c, int64_t vbase)
 {
-    const int64_t lin = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
-    Cell c;
-    c.nv = c.nt = 0; c.entry = -1;
-    int i = 0, j = 0, k = 0;
-    if (lin < nnode) {
-        cell_coords(p, lin, i, j, k);
-        classify(p, i, j, k, c);
-    }
-    unsigned ea, eb, ta, tb;
-    block_scan2((unsigned)c.nv, 0u, ea, eb, ta, tb);
-    if (c.nv == 0) return;
-    const int64_t vbase = (int64_t)block_prefix[blockIdx.x].x + ea;
     const uint8_t *rank = p.tb.edge_rank + 13 * c.entry;
 #pragma unroll 1
     for (int e = 0; e < 12; ++e) {
@@ -305,9 +307,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_verts_kernel(McParams p, i
     }
 }
 
-__global__ void __launch_bounds__(MC_THREADS) mc_emit_faces_kernel(McParams p, int64_t nnode, const uint2 *block_prefix,
-                                                                   const int32_t *__restrict__ vid, const int32_t *__restrict__ seam_in,
-                                                                   int64_t id_offset, int32_t *__restrict__ faces)
+__global__ void __launch_bounds__(MC_THREADS) mc_emit_verts_kernel(McParams p, int64_t nnode, const uint2 *block_prefix, McOut o)
 {
     const int64_t lin = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
     Cell c;
@@ -318,10 +318,16 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_faces_kernel(McParams p, i
         classify(p, i, j, k, c);
     }
     unsigned ea, eb, ta, tb;
-    block_scan2((unsigned)c.nv, (unsigned)c.nt, ea, eb, ta, tb);
-    if (c.nt == 0) return;
-    const uint2 pre = block_prefix[blockIdx.x];
-    const int64_t fbase = (int64_t)pre.y + eb;
+    block_scan2((unsigned)c.nv, 0u, ea, eb, ta, tb);
+    if (c.nv == 0) return;
+    emit_cell_verts(p, o, i, j, k, c, (int64_t)block_prefix[blockIdx.x].x + ea);
+}
+
+// all faces of cell (i,j,k); vbase / fbase = its first vertex / face in this volume's lists
+__device__ __forceinline__ void emit_cell_faces(const McParams &p, int i, int j, int k, const Cell &c, int64_t vbase, int64_t fbase,
+                                                const int32_t *__restrict__ vid, const int32_t *__restrict__ seam_in,
+                                                int64_t id_offset, int32_t *__restrict__ faces)
+{
     const uint8_t *rank = p.tb.edge_rank + 13 * c.entry;
     const uint8_t *te = p.tb.tri_edges + 3 * (int)p.tb.tri_off[c.entry];
     int32_t centre_id = -1;
@@ -329,7 +335,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_faces_kernel(McParams p, i
         int r = 0;
         for (int e2 = 0; e2 < 12; ++e2)
             if (((c.owned >> e2) & 1u) && rank[e2] < rank[12]) ++r;
-        centre_id = (int32_t)((int64_t)pre.x + ea + r + id_offset);
+        centre_id = (int32_t)(vbase + r + id_offset);
     }
     for (int t = 0; t < c.nt; ++t) {
         int32_t tri[3];
@@ -350,6 +356,25 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_faces_kernel(McParams p, i
     }
 }
 
+__global__ void __launch_bounds__(MC_THREADS) mc_emit_faces_kernel(McParams p, int64_t nnode, const uint2 *block_prefix,
+                                                                   const int32_t *__restrict__ vid, const int32_t *__restrict__ seam_in,
+                                                                   int64_t id_offset, int32_t *__restrict__ faces)
+{
+    const int64_t lin = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
+    Cell c;
+    c.nv = c.nt = 0; c.entry = -1;
+    int i = 0, j = 0, k = 0;
+    if (lin < nnode) {
+        cell_coords(p, lin, i, j, k);
+        classify(p, i, j, k, c);
+    }
+    unsigned ea, eb, ta, tb;
+    block_scan2((unsigned)c.nv, (unsigned)c.nt, ea, eb, ta, tb);
+    if (c.nt == 0) return;
+    const uint2 pre = block_prefix[blockIdx.x];
+    emit_cell_faces(p, i, j, k, c, (int64_t)pre.x + ea, (int64_t)pre.y + eb, vid, seam_in, id_offset, faces);
+}
+
 // ids of the vertices lying in the last plane of axis 0 (for the slab above): [2][R1][R2]
 __global__ void mc_seam_export_kernel(McParams p, const int32_t *__restrict__ vid, int32_t *__restrict__ seam_out)
 {
@@ -368,6 +393,187 @@ __global__ void mc_seam_export_kernel(McParams p, const int32_t *__restrict__ vi
     }
     seam_out[(int64_t)j * p.R2 + k] = a1;
     seam_out[((int64_t)p.R1 + j) * p.R2 + k] = a2;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast path (R2 % 4 == 0): every thread looks at 4 consecutive cells of a k-row with 4 aligned
+// float4 loads (+ 4 scalars), rejects the all-inside / all-outside case on 20 sign bits, and only
+// surface cells go through classify_vals.  A first pass counts, a second pass writes the compact,
+// scan-ordered list of active cells (with their vertex / face offsets); vertices and faces are
+// then emitted by one thread per ACTIVE cell, so the volume is read twice and never again.
+// ------------------------------------------------------------------------------------------
+struct CellRec { uint32_t lin, vbase, fbase, pad; };
+
+struct Quad {
+    int i, j, k0;
+    int ncell;              // number of valid cells among k0 .. k0+3
+    unsigned bits;          // sign bits: 5 per row, rows (0,0) (0,1) (1,0) (1,1)
+    float v[4][5];
+};
+
+__device__ __forceinline__ bool load_quad(const McParams &p, float level, uint32_t q, uint32_t nquad, Quad &Q)
+{
+    Q.ncell = 0;
+    if (q >= nquad) return false;
+    const uint32_t qrow = (uint32_t)p.R2 >> 2;
+    Q.k0 = (int)(q % qrow) * 4;
+    const uint32_t t = q / qrow;
+    Q.j = (int)(t % (uint32_t)p.R1);
+    Q.i = (int)(t / (uint32_t)p.R1);
+    if (Q.i >= p.R0 - 1 || Q.j >= p.R1 - 1) return false;
+    Q.ncell = min(4, p.R2 - 1 - Q.k0);
+    unsigned bits = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float *row = p.vol + node_lin(p, Q.i + (r >> 1), Q.j + (r & 1), Q.k0);
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(row));
+        Q.v[r][0] = a.x; Q.v[r][1] = a.y; Q.v[r][2] = a.z; Q.v[r][3] = a.w;
+        Q.v[r][4] = Q.k0 + 4 < p.R2 ? __ldg(row + 4) : a.w;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) bits |= (Q.v[r][c] > level ? 1u : 0u) << (5 * r + c);
+    }
+    Q.bits = bits;
+    return bits != 0u && bits != 0xFFFFFu;
+}
+
+// cell t of the quad: corner values in Lewiner order; returns false when the cell has no surface
+__device__ __forceinline__ bool quad_cell(const Quad &Q, int t, float (&val)[8])
+{
+    const unsigned b = Q.bits >> t;
+    const unsigned cas = (b & 1u) | ((b >> 1) & 1u) << 1 | ((b >> 6) & 1u) << 2 | ((b >> 5) & 1u) << 3 |
+                         ((b >> 10) & 1u) << 4 | ((b >> 11) & 1u) << 5 | ((b >> 16) & 1u) << 6 | ((b >> 15) & 1u) << 7;
+    if (cas == 0u || cas == 255u) return false;
+    val[0] = Q.v[0][t]; val[1] = Q.v[0][t + 1]; val[2] = Q.v[1][t + 1]; val[3] = Q.v[1][t];
+    val[4] = Q.v[2][t]; val[5] = Q.v[2][t + 1]; val[6] = Q.v[3][t + 1]; val[7] = Q.v[3][t];
+    return true;
+}
+
+__device__ __forceinline__ void block_scan3(uint3 a, uint3 &excl, uint3 &tot)
+{
+    __shared__ uint3 wsum[MC_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint3 inc = a;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned x = __shfl_up_sync(0xffffffffu, inc.x, o), y = __shfl_up_sync(0xffffffffu, inc.y, o), z = __shfl_up_sync(0xffffffffu, inc.z, o);
+        if (lane >= o) { inc.x += x; inc.y += y; inc.z += z; }
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint3 off = make_uint3(0, 0, 0), sum = make_uint3(0, 0, 0);
+#pragma unroll
+    for (int w = 0; w < MC_THREADS / 32; ++w) {
+        if (w == warp) off = sum;
+        sum.x += wsum[w].x; sum.y += wsum[w].y; sum.z += wsum[w].z;
+    }
+    excl = make_uint3(off.x + inc.x - a.x, off.y + inc.y - a.y, off.z + inc.z - a.z);
+    tot = sum;
+    __syncthreads();
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(MC_THREADS) mc_quad_kernel(McParams p, float level, uint32_t nquad, uint4 *block_tot,
+                                                             unsigned long long *n_amb, CellRec *cells)
+{
+    const uint32_t q = blockIdx.x * MC_THREADS + threadIdx.x;
+    Quad Q;
+    uint3 mine = make_uint3(0, 0, 0);
+    unsigned amb = 0;
+    unsigned nv[4] = {0, 0, 0, 0}, nt[4] = {0, 0, 0, 0};
+    const bool any = load_quad(p, level, q, nquad, Q);
+    if (any) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float val[8];
+            if (t < Q.ncell && quad_cell(Q, t, val)) {
+                Cell c;
+                classify_vals(p, Q.i, Q.j, Q.k0 + t, val, c);
+                nv[t] = (unsigned)c.nv; nt[t] = (unsigned)c.nt;
+                if (c.nt | c.nv) { mine.x += 1; mine.y += nv[t]; mine.z += nt[t]; }
+                amb += c.ambiguous;
+            }
+        }
+    }
+    uint3 excl, tot;
+    block_scan3(mine, excl, tot);
+    if (!WRITE) {
+        const unsigned a = __syncthreads_count(amb) ? 1u : 0u;
+        (void)a;
+        if (amb) atomicAdd(n_amb, (unsigned long long)amb);
+        if (threadIdx.x == 0) block_tot[blockIdx.x] = make_uint4(tot.x, tot.y, tot.z, 0);
+    } else if (mine.x) {
+        const uint4 pre = block_tot[blockIdx.x];
+        uint32_t a = pre.x + excl.x, vb = pre.y + excl.y, fb = pre.z + excl.z;
+        const uint32_t lin0 = q * 4;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (nv[t] | nt[t]) {
+                CellRec r;
+                r.lin = lin0 + t; r.vbase = vb; r.fbase = fb; r.pad = 0;
+                cells[a++] = r;
+                vb += nv[t]; fb += nt[t];
+            }
+    }
+}
+
+__global__ void __launch_bounds__(1024) mc_scan_blocks3_kernel(uint4 *block_tot, int64_t nblocks, unsigned long long *totals)
+{
+    __shared__ unsigned long long wsum[3][32];
+    __shared__ unsigned long long carry[3];
+    if (threadIdx.x < 3) carry[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < nblocks; base += 1024) {
+        const int64_t idx = base + threadIdx.x;
+        const uint4 v = idx < nblocks ? block_tot[idx] : make_uint4(0, 0, 0, 0);
+        unsigned long long a[3] = {v.x, v.y, v.z};
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const unsigned long long x = __shfl_up_sync(0xffffffffu, a[c], o);
+                if (lane >= o) a[c] += x;
+            }
+        if (lane == 31)
+            for (int c = 0; c < 3; ++c) wsum[c][warp] = a[c];
+        __syncthreads();
+        unsigned long long off[3] = {carry[0], carry[1], carry[2]};
+        for (int w = 0; w < warp; ++w)
+            for (int c = 0; c < 3; ++c) off[c] += wsum[c][w];
+        if (idx < nblocks)
+            block_tot[idx] = make_uint4((unsigned)(off[0] + a[0] - v.x), (unsigned)(off[1] + a[1] - v.y), (unsigned)(off[2] + a[2] - v.z), 0);
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            for (int c = 0; c < 3; ++c) carry[c] = off[c] + a[c];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { totals[0] = carry[1]; totals[1] = carry[2]; totals[2] = carry[0]; }
+}
+
+__global__ void __launch_bounds__(128) mc_list_verts_kernel(McParams p, const CellRec *__restrict__ cells, uint32_t nact, McOut o)
+{
+    const uint32_t a = blockIdx.x * 128 + threadIdx.x;
+    if (a >= nact) return;
+    const CellRec r = cells[a];
+    int i, j, k;
+    cell_coords(p, (int64_t)r.lin, i, j, k);
+    Cell c;
+    classify(p, i, j, k, c);
+    if (c.nv) emit_cell_verts(p, o, i, j, k, c, (int64_t)r.vbase);
+}
+
+__global__ void __launch_bounds__(128) mc_list_faces_kernel(McParams p, const CellRec *__restrict__ cells, uint32_t nact,
+                                                            const int32_t *__restrict__ vid, const int32_t *__restrict__ seam_in,
+                                                            int64_t id_offset, int32_t *__restrict__ faces)
+{
+    const uint32_t a = blockIdx.x * 128 + threadIdx.x;
+    if (a >= nact) return;
+    const CellRec r = cells[a];
+    int i, j, k;
+    cell_coords(p, (int64_t)r.lin, i, j, k);
+    Cell c;
+    classify(p, i, j, k, c);
+    if (c.nt) emit_cell_faces(p, i, j, k, c, (int64_t)r.vbase, (int64_t)r.fbase, vid, seam_in, id_offset, faces);
 }
 
 struct TableBlob {
@@ -428,13 +634,41 @@ extern "C" int surs_mc_count(surs_ctx *ctx, const float *vol, const int res[3], 
     memcpy(ctx->mc_res, res, sizeof(int) * 3);
     ctx->mc_level = level;
     ctx->mc_flags = flags;
-    const int64_t nblocks = (nnode + MC_THREADS - 1) / MC_THREADS;
-    if (surs_ensure(ctx, (void **)&ctx->mc_block_tot, &ctx->mc_block_cap, sizeof(uint2) * (size_t)nblocks)) return 1;
     SURS_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, 64, st));
     McParams p = make_params(ctx);
-    mc_count_kernel<<<(unsigned)nblocks, MC_THREADS, 0, st>>>(p, nnode, ctx->mc_block_tot, ctx->counter + 1);
+    static const bool no_fast = getenv("SURS_MC_SLOW") != nullptr;
+    ctx->mc_fast = (res[2] % 4 == 0) && ((uintptr_t)vol % 16 == 0) && !no_fast;
+    if (ctx->mc_fast) {
+        const uint32_t nquad = (uint32_t)(nnode / 4);
+        const int64_t nb = ((int64_t)nquad + MC_THREADS - 1) / MC_THREADS;
+        if (surs_ensure(ctx, (void **)&ctx->mc_block_tot, &ctx->mc_block_cap, sizeof(uint4) * (size_t)nb)) return 1;
+        uint4 *bt = reinterpret_cast<uint4 *>(ctx->mc_block_tot);
+        mc_quad_kernel<false><<<(unsigned)nb, MC_THREADS, 0, st>>>(p, level, nquad, bt, ctx->counter + 1, nullptr);
+        SURS_LAUNCH_CHECK(ctx, "mc_quad_kernel<count>");
+        mc_scan_blocks3_kernel<<<1, 1024, 0, st>>>(bt, nb, ctx->counter + 2);
+        SURS_LAUNCH_CHECK(ctx, "mc_scan_blocks3_kernel");
+        unsigned long long host[5];
+        SURS_CUDA(ctx, cudaMemcpyAsync(host, ctx->counter, sizeof(host), cudaMemcpyDeviceToHost, st));
+        SURS_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->mc_nv = (int64_t)host[2];
+        ctx->mc_nf = (int64_t)host[3];
+        ctx->mc_nact = (int64_t)host[4];
+        if (ctx->mc_nv >= ((int64_t)1 << 31) || ctx->mc_nf >= ((int64_t)1 << 31)) SURS_FAIL(ctx, "surs_mc_count: mesh too large for int32 indices");
+        if (ctx->mc_nact > 0) {
+            if (surs_ensure(ctx, (void **)&ctx->mc_cells, &ctx->mc_cells_cap, sizeof(CellRec) * (size_t)ctx->mc_nact)) return 1;
+            mc_quad_kernel<true><<<(unsigned)nb, MC_THREADS, 0, st>>>(p, level, nquad, bt, nullptr, reinterpret_cast<CellRec *>(ctx->mc_cells));
+            SURS_LAUNCH_CHECK(ctx, "mc_quad_kernel<compact>");
+        }
+        if (n_verts) *n_verts = ctx->mc_nv;
+        if (n_faces) *n_faces = ctx->mc_nf;
+        if (n_ambiguous) *n_ambiguous = (int64_t)host[1];
+        return 0;
+    }
+    const int64_t nblocks = (nnode + MC_THREADS - 1) / MC_THREADS;
+    if (surs_ensure(ctx, (void **)&ctx->mc_block_tot, &ctx->mc_block_cap, sizeof(uint2) * (size_t)nblocks)) return 1;
+    mc_count_kernel<<<(unsigned)nblocks, MC_THREADS, 0, st>>>(p, nnode, reinterpret_cast<uint2 *>(ctx->mc_block_tot), ctx->counter + 1);
     SURS_LAUNCH_CHECK(ctx, "mc_count_kernel");
-    mc_scan_blocks_kernel<<<1, 1024, 0, st>>>(ctx->mc_block_tot, nblocks, ctx->counter + 2);
+    mc_scan_blocks_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<uint2 *>(ctx->mc_block_tot), nblocks, ctx->counter + 2);
     SURS_LAUNCH_CHECK(ctx, "mc_scan_blocks_kernel");
     unsigned long long host[4];
     SURS_CUDA(ctx, cudaMemcpyAsync(host, ctx->counter, sizeof(host), cudaMemcpyDeviceToHost, st));
@@ -470,8 +704,12 @@ extern "C" int surs_mc_emit_verts(surs_ctx *ctx, const double *mat, float *verts
     o.id_offset = vert_id_offset;
     o.plane_offset = plane_offset;
     ctx->mc_id_offset = vert_id_offset;
-    if (ctx->mc_nv > 0) {
-        mc_emit_verts_kernel<<<(unsigned)nblocks, MC_THREADS, 0, st>>>(p, nnode, ctx->mc_block_tot, o);
+    if (ctx->mc_nv > 0 && ctx->mc_fast) {
+        mc_list_verts_kernel<<<(unsigned)((ctx->mc_nact + 127) / 128), 128, 0, st>>>(p, reinterpret_cast<const CellRec *>(ctx->mc_cells),
+                                                                                     (uint32_t)ctx->mc_nact, o);
+        SURS_LAUNCH_CHECK(ctx, "mc_list_verts_kernel");
+    } else if (ctx->mc_nv > 0) {
+        mc_emit_verts_kernel<<<(unsigned)nblocks, MC_THREADS, 0, st>>>(p, nnode, reinterpret_cast<const uint2 *>(ctx->mc_block_tot), o);
         SURS_LAUNCH_CHECK(ctx, "mc_emit_verts_kernel");
     }
     if (seam_out) {
@@ -493,9 +731,14 @@ extern "C" int surs_mc_emit_faces(surs_ctx *ctx, int32_t *faces, const int32_t *
     const int64_t nnode = (int64_t)ctx->mc_res[0] * ctx->mc_res[1] * ctx->mc_res[2];
     const int64_t nblocks = (nnode + MC_THREADS - 1) / MC_THREADS;
     McParams p = make_params(ctx);
-    if (ctx->mc_nf > 0) {
-        mc_emit_faces_kernel<<<(unsigned)nblocks, MC_THREADS, 0, st>>>(p, nnode, ctx->mc_block_tot, ctx->mc_vid, seam_in,
-                                                                      ctx->mc_id_offset, faces);
+    if (ctx->mc_nf > 0 && ctx->mc_fast) {
+        mc_list_faces_kernel<<<(unsigned)((ctx->mc_nact + 127) / 128), 128, 0, st>>>(p, reinterpret_cast<const CellRec *>(ctx->mc_cells),
+                                                                                     (uint32_t)ctx->mc_nact, ctx->mc_vid, seam_in,
+                                                                                     ctx->mc_id_offset, faces);
+        SURS_LAUNCH_CHECK(ctx, "mc_list_faces_kernel");
+    } else if (ctx->mc_nf > 0) {
+        mc_emit_faces_kernel<<<(unsigned)nblocks, MC_THREADS, 0, st>>>(p, nnode, reinterpret_cast<const uint2 *>(ctx->mc_block_tot), ctx->mc_vid,
+                                                                      seam_in, ctx->mc_id_offset, faces);
         SURS_LAUNCH_CHECK(ctx, "mc_emit_faces_kernel");
     }
     return 0;

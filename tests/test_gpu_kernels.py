@@ -50,6 +50,17 @@ def znum(case):
     return float(case.load_size // 2), float(case.z_size)
 
 
+def test_umma_cta_pair_selftest(ctx):
+    """tcgen05.mma.cta_group::2 (one cluster of two CTAs, M = 256): building block for the next kernels."""
+    from surs_b200 import _capi
+    g = torch.Generator().manual_seed(1)
+    for (N, K) in ((256, 64), (256, 128), (128, 192), (64, 64)):
+        A = torch.randn(256, K, generator=g)
+        B = torch.randn(N, K, generator=g)
+        D = _capi.selftest_umma2(ctx, A, B).cpu()
+        assert (D - A.half().float() @ B.half().float().T).abs().max().item() < 2e-3, (N, K)
+
+
 def test_umma_selftest(ctx):
     """The tcgen05 plumbing in isolation: descriptors, swizzled K-major layout, TMEM read-back."""
     g = torch.Generator().manual_seed(0)
@@ -202,6 +213,7 @@ def test_marching_cubes_matches_cpu_twin(ctx):
     noisy[0] = noisy[-1] = 0; noisy[:, 0] = noisy[:, -1] = 0; noisy[:, :, 0] = noisy[:, :, -1] = 0
     v, f = _mc_check(ctx, noisy)
     helpers.mesh_euler_closed(v, f)
+    _mc_check(ctx, np.ascontiguousarray(noisy[:, :, :27]))          # last axis not a multiple of 4: general kernels
     g = np.stack(np.meshgrid(*[np.arange(40)] * 3, indexing="ij")).astype(np.float64)
     wavy = (np.sin(g[0] * 0.7) + np.sin(g[1] * 0.9) + np.sin(g[2] * 0.8)).astype(np.float32)   # open surface at the border
     _mc_check(ctx, wavy, level=0.1)
