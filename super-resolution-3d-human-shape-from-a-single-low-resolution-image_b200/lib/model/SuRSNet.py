@@ -40,7 +40,7 @@ def _fingerprint(tensors):
 
 
 class SuRSNet(nn.Module):
-    def __init__(self, opt, projection_mode="orthogonal", error_term=None, encoder=None, precision=_capi.PREC_FP16):
+    def __init__(self, opt, projection_mode="orthogonal", error_term=None, encoder="auto", precision=_capi.PREC_FP16):
         super().__init__()
         self.name = "surs_b200"
         self.opt = opt
@@ -52,6 +52,21 @@ class SuRSNet(nn.Module):
         self.precision = precision
         self.mlp_lr = SurfaceClassifier(opt.mlp_dim_lr, opt.num_views, opt.no_residual, opt.mlp_res_layers_lr, nn.Sigmoid())
         self.mlp_hr = SurfaceClassifier(opt.mlp_dim_hr, opt.num_views, opt.no_residual, opt.mlp_res_layers_hr, nn.Sigmoid())
+        # encoder: "auto" = the built-in PyTorch modules (reference names, so reference checkpoints load
+        # with strict=True) when opt describes them; None = query side only; or any object with
+        # super_res / filter_lr / filter_hr
+        if encoder == "auto":
+            encoder = "builtin" if hasattr(opt, "num_stack_lr") else None
+        if encoder == "builtin":
+            from .encoder import HGFilter, SuRSSR_v3, init_weights
+            self.image_filter_lr = HGFilter(opt.num_stack_lr, opt.hg_depth, 256, opt.hg_dim, opt.norm, "low_res", False)
+            self.image_filter_hr = HGFilter(opt.num_stack_hr, opt.hg_depth, 64, opt.hg_dim, opt.norm, "high_res", False)
+            self.super_resolution = SuRSSR_v3(opt)
+            init_weights(self)
+            encoder = None
+            self._builtin = True
+        else:
+            self._builtin = False
         self.encoder = encoder
         self.im_feat_list_lr = []
         self.im_feat_list_hr = []
@@ -67,6 +82,8 @@ class SuRSNet(nn.Module):
 
     # ------------------------------------------------------------------ encoder side (PyTorch)
     def _need_encoder(self):
+        if self._builtin:
+            return self
         if self.encoder is None:
             raise RuntimeError("this SuRSNet was built without an image encoder; pass encoder= or set "
                                "im_feat_list_lr / im_feat_list_hr yourself")
@@ -74,18 +91,21 @@ class SuRSNet(nn.Module):
 
     def super_res(self, images):
         """reference lib/model/SuRSNet.py:124-129."""
-        self.im_SR, self.feature_lr, self.feature_hr = self._need_encoder().super_res(images)
+        enc = self._need_encoder()
+        self.im_SR, self.feature_lr, self.feature_hr = self.super_resolution(images) if enc is self else enc.super_res(images)
         return self.im_SR, self.feature_lr, self.feature_hr
 
     def filter_lr(self, images):
         """reference lib/model/SuRSNet.py:101-110: keeps only the last hourglass output in eval mode."""
-        self.im_feat_list_lr = self._need_encoder().filter_lr(images)
+        enc = self._need_encoder()
+        self.im_feat_list_lr = self.image_filter_lr(images) if enc is self else enc.filter_lr(images)
         if not self.training:
             self.im_feat_list_lr = [self.im_feat_list_lr[-1]]
 
     def filter_hr(self, images):
         """reference lib/model/SuRSNet.py:112-122."""
-        self.im_feat_list_hr = self._need_encoder().filter_hr(images)
+        enc = self._need_encoder()
+        self.im_feat_list_hr = self.image_filter_hr(images) if enc is self else enc.filter_hr(images)
         if not self.training:
             self.im_feat_list_hr = [self.im_feat_list_hr[-1]]
 

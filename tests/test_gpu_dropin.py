@@ -173,3 +173,24 @@ def test_gen_mesh_writes_reference_obj(case32, tmp_path):
         assert fh.read() == O.obj_text(out[0], out[1])
     with open(path[:-4] + "_LR.obj") as fh:
         assert fh.read() == O.obj_text(out[4], out[5])
+
+
+def test_gen_mesh_with_builtin_encoder(tmp_path):
+    """The whole reference flow (lib/train_util.py:53-85) with the PyTorch encoder + CUDA reconstruction."""
+    opt = helpers.make_opt(loadSize=128, num_stack_lr=3, num_stack_hr=1, hg_depth=2, hg_dim=256, norm="group",
+                           n_block=[2, 2, 2], rgb_range=255, scale=2, residual=True, resolution=64)
+    torch.manual_seed(0)
+    net = SuRSNet(opt).to(DEV).eval()
+    for mlp in (net.mlp_lr, net.mlp_hr):                     # widen the occupancy range of the random-init MLPs
+        for conv in mlp.layers():
+            conv.weight.data *= 6.0
+    g = torch.Generator().manual_seed(1)
+    data = {"img_LR": torch.rand(1, 3, 64, 64, generator=g) * 2 - 1, "b_min": np.array([-0.5] * 3), "b_max": np.array([0.5] * 3)}
+    path = str(tmp_path / "person.obj")
+    with torch.no_grad():
+        train_util.gen_mesh(opt, net, DEV, data, path, use_octree=True)
+    assert net.im_feat_list_lr[0].shape == (1, 256, 32, 32) and net.im_feat_list_hr[0].shape == (1, 64, 128, 128)
+    for suffix in ("_HR.obj", "_LR.obj"):
+        with open(path[:-4] + suffix) as fh:
+            lines = fh.read().splitlines()
+        assert lines[0].startswith("v ") and lines[-1].startswith("f ") and len(lines) > 100
