@@ -57,6 +57,16 @@ def reconstruction(*args, **kwargs):
 
 def _reconstruction(opt, net, cuda, calib_tensor, resolution, b_min, b_max, use_octree, num_samples, transform,
                     precision, return_stats):
+    import os, time
+    _T = os.environ.get("SURS_TIMING") is not None
+    _t = [time.perf_counter()]
+
+    def _tick(label):
+        if _T:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            print("[surs timing] %-22s %8.2f ms" % (label, (now - _t[0]) * 1e3))
+            _t[0] = now
     b_min = np.asarray(b_min, dtype=np.float64).reshape(3)
     b_max = np.asarray(b_max, dtype=np.float64).reshape(3)
     stats = {}
@@ -95,10 +105,13 @@ def _reconstruction(opt, net, cuda, calib_tensor, resolution, b_min, b_max, use_
         ctx = net.surs_context() if _is_accelerated(net) else _default_context(cuda)
         vol_hr = torch.from_numpy(sdf_hr.astype(np.float32)).to(ctx.device)
         vol_lr = torch.from_numpy(sdf_lr.astype(np.float32)).to(ctx.device)
+    _tick("grid evaluation")
     m34 = mat[:3, :4]
     w_hr, f_hr, n_hr, v_hr, amb_hr = _mesh_from_volume(ctx, vol_hr, m34)
     w_lr, f_lr, n_lr, v_lr, amb_lr = _mesh_from_volume(ctx, vol_lr, m34)
+    _tick("marching cubes x2")
     host = _to_host([w_hr, f_hr, n_hr, v_hr, w_lr, f_lr, n_lr, v_lr])
+    _tick("device -> host")
     out_hr, out_lr = tuple(host[:4]), tuple(host[4:])
     if return_stats:
         stats["ambiguous_cells"] = (amb_hr, amb_lr)

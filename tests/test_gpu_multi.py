@@ -1,0 +1,64 @@
+"""Multi-GPU slab reconstruction == single-GPU reconstruction, bit for bit (needs >= 2 GPUs;
+skipped on the single-GPU test box, run with `gpurun --gpus 2 -- pytest tests/test_gpu_multi.py -m gpu`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, res, out):
+    from surs_b200 import _capi, parallel, synthetic as syn
+    from surs_b200.lib import sdf as bsdf
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        dev = torch.device("cuda", rank)
+        case = syn.SyntheticCase(S=32, seed=0)
+        ctx = _capi.Context(dev)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        ctx.set_weights([t(w) for w in case.mlp_lr[0]], [t(b) for b in case.mlp_lr[1]], [t(w) for w in case.mlp_hr[0]], [t(b) for b in case.mlp_hr[1]],
+                        syn.MLP_DIM_LR, syn.MLP_DIM_HR, syn.RES_LAYERS)
+        ctx.set_features(t(case.feat_lr), t(case.feat_hr))
+        zn, zd = float(case.load_size // 2), float(case.z_size)
+        bmin, bmax = np.array([-0.5] * 3), np.array([0.5] * 3)
+        mat = bsdf.grid_matrix(res, bmin, bmax)[:3, :4]
+        got = parallel.reconstruct_slab(ctx, (res,) * 3, bmin, bmax, case.calib, zn, zd, mat)
+        ok = True
+        if rank == 0:
+            vols = ctx.eval_grid((res,) * 3, bmin, bmax, case.calib, zn, zd)
+            for (w, f, n, v), vol in zip(got, vols):
+                _, w1, f1, n1, v1, _ = ctx.marching_cubes(vol, 0.5, mat)
+                ok = ok and torch.equal(w, w1) and torch.equal(f, f1) and torch.equal(v, v1) and torch.equal(n, n1)
+        out.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_reconstruction_equals_single_gpu(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 96, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
