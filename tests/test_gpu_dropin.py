@@ -184,8 +184,10 @@ def test_gen_mesh_with_builtin_encoder(tmp_path):
     for mlp in (net.mlp_lr, net.mlp_hr):                     # widen the occupancy range of the random-init MLPs
         for conv in mlp.layers():
             conv.weight.data *= 6.0
+        mlp.conv4.bias.data += 0.3                           # inside the image: occupancy > 0.5 ...
     g = torch.Generator().manual_seed(1)
-    data = {"img_LR": torch.rand(1, 3, 64, 64, generator=g) * 2 - 1, "b_min": np.array([-0.5] * 3), "b_max": np.array([0.5] * 3)}
+    # ... and the box is larger than the image, where the mask forces occupancy 0: a surface always exists
+    data = {"img_LR": torch.rand(1, 3, 64, 64, generator=g) * 2 - 1, "b_min": np.array([-0.7] * 3), "b_max": np.array([0.7] * 3)}
     path = str(tmp_path / "person.obj")
     with torch.no_grad():
         train_util.gen_mesh(opt, net, DEV, data, path, use_octree=True)
