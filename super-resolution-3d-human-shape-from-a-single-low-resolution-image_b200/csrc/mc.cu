@@ -497,8 +497,6 @@ __global__ void __launch_bounds__(MC_THREADS) mc_quad_kernel(McParams p, float l
     uint3 excl, tot;
     block_scan3(mine, excl, tot);
     if (!WRITE) {
-        const unsigned a = __syncthreads_count(amb) ? 1u : 0u;
-        (void)a;
         if (amb) atomicAdd(n_amb, (unsigned long long)amb);
         if (threadIdx.x == 0) block_tot[blockIdx.x] = make_uint4(tot.x, tot.y, tot.z, 0);
     } else if (mine.x) {

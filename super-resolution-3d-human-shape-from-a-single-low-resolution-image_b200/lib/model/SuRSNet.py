@@ -7,9 +7,9 @@ that are empty stubs in the reference (lib/model/BaseSuRSNet.py:50-56,66-78).
 
 The two SurfaceClassifier MLPs keep the reference's state-dict keys
 (``mlp_{lr,hr}.conv{0..4}.{weight,bias}``), so a reference checkpoint's MLP part loads unchanged.
-The image encoder (SuRSSR_v3 + HGFilter, kept in PyTorch by design) is pluggable: pass
-``encoder=`` (any module with ``super_res`` / ``filter_lr`` / ``filter_hr`` semantics) or use
-``lib.model.encoder.build_encoder(opt)``.
+The image encoder (SuRSSR_v3 + HGFilter, kept in PyTorch by design; ``lib/model/encoder.py`` holds a
+state-dict-compatible one, built when ``encoder="auto"`` finds the encoder options in ``opt``) is
+pluggable: pass ``encoder=`` (any module with ``super_res`` / ``filter_lr`` / ``filter_hr`` semantics).
 
 Query semantics (reference lib/model/SuRSNet.py:131-187): ``query_mr`` computes the LR
 prediction, ``query_sr`` appends the MASKED LR prediction as channel 321 and computes the HR one;

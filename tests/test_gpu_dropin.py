@@ -196,3 +196,34 @@ def test_gen_mesh_with_builtin_encoder(tmp_path):
         with open(path[:-4] + suffix) as fh:
             lines = fh.read().splitlines()
         assert lines[0].startswith("v ") and lines[-1].startswith("f ") and len(lines) > 100
+
+
+def test_eval_cli_end_to_end(tmp_path):
+    """apps/eval_SuRS.py: image folder + checkpoint file -> OBJ files (reference flags)."""
+    import importlib.util
+    from PIL import Image
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("eval_surs_app", os.path.join(root, "apps", "eval_SuRS.py"))
+    app = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(app)
+    from surs_b200.lib.options import BaseOptions
+    os.makedirs(tmp_path / "data" / "image_final")
+    os.makedirs(tmp_path / "data" / "mask_final")
+    rng = np.random.default_rng(0)
+    for name in ("p0", "p1"):
+        Image.fromarray(rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)).save(tmp_path / "data" / "image_final" / (name + ".png"))
+        Image.fromarray(np.full((64, 64), 255, np.uint8)).save(tmp_path / "data" / "mask_final" / (name + ".png"))
+    args = ["--dataroot", str(tmp_path / "data"), "--results_path", str(tmp_path / "res"), "--name", "t", "--residual",
+            "--resolution", "64", "--loadSize", "128", "--b_min", "-0.7", "-0.7", "-0.7", "--b_max", "0.7", "0.7", "0.7"]
+    torch.manual_seed(0)
+    net = SuRSNet(BaseOptions().parse(args))
+    for mlp in (net.mlp_lr, net.mlp_hr):
+        for conv in mlp.layers():
+            conv.weight.data *= 6.0
+        mlp.conv4.bias.data += 0.3
+    ckpt = str(tmp_path / "netG_epoch_12")
+    torch.save(net.state_dict(), ckpt)                     # the reference's checkpoint format (flat state_dict)
+    done = app.main(args + ["--load_netG_checkpoint_path", ckpt])
+    assert len(done) == 2
+    for p in done:
+        assert os.path.getsize(p[:-4] + "_HR.obj") > 1000 and os.path.getsize(p[:-4] + "_LR.obj") > 1000
