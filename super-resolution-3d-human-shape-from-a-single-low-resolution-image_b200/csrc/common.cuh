@@ -200,5 +200,6 @@ int surs_launch_query_tc(surs_ctx *ctx, const PointIO &io, cudaStream_t st);
 // query_col.cu
 int surs_col_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS], cudaStream_t st);
 int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st);
+int surs_launch_query_inc(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st);
 // mc.cu
 int surs_mc_init_tables(surs_ctx *ctx);

@@ -22,28 +22,17 @@
 //
 // Warp roles (main kernel): 0-7 produce y0 and run the epilogues (warp w: TMEM lanes 32 (w%4)..,
 // column half w/4), 8 = MMA issue, 9 = weight stream + per-column vectors (bulk TMA).
-#include "tc_common.cuh"
+#include "col_common.cuh"
 
 #include <stdlib.h>
 
 namespace {
 
-using namespace tc;
+using namespace col;
 
-// ---- per-column vectors (fp32), per MLP ---------------------------------------------------
-constexpr int CV_C0 = 0, CV_C2 = 1024, CV_C3 = 1280, CV_C4 = 1408, CV_STRIDE = 1412;
-constexpr int CV_FLOATS = 2 * CV_STRIDE;                 // both MLPs
-constexpr int CV_BYTES = CV_FLOATS * 4;                  // 11296 B per column
-// ---- per-MLP constant vectors (fp32) --------------------------------------------------------
-constexpr int GV_WZ0 = 0, GV_WP0 = 1024, GV_B1 = 2048, GV_WZ2 = 2560, GV_WP2 = 2816, GV_WZ3 = 3072, GV_WP3 = 3200,
-              GV_W4Y = 3328, GV_WZ4 = 3456, GV_WP4 = 3457, GV_STRIDE = 3460;
-constexpr int GV_BYTES = 2 * GV_STRIDE * 4;              // 27680 B
-
-constexpr int W128_BLK_BYTES = 128 * 128;                // layer 3: 128 rows x 64 fp16
 constexpr int NSTAGE = 4;
 constexpr int NA_SLOT = 3;
 constexpr int BLOCKS_PER_MLP = 32 + 8 + 4;
-constexpr size_t MLP_BYTES = (size_t)40 * W_BLK_BYTES + 4 * (size_t)W128_BLK_BYTES;
 constexpr int KBLK_PER_MLP = 16 + 4 + 4 + 4;             // A-ring K blocks per MLP
 constexpr int NEPI = 8;
 constexpr int NTHREADS = (NEPI + 2) * 32;
@@ -68,7 +57,7 @@ struct Bars {
 struct ColParams {
     const uint8_t *weights;        // 2 x MLP_BYTES
     const float *gv;               // [2][GV_STRIDE]
-    const float *table;            // [ncols][CV_FLOATS]
+    const float *table;            // [ncols][CV_ROW_FLOATS]
     int64_t ntiles;
     int nseg;                      // tiles per column = ceil(R2 / 128)
     int R1, R2, plane_lo;
@@ -365,7 +354,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 const uint32_t cvb = it & 1u;
                 ptx::mbar_wait(&bars->cv_empty[cvb], ((it >> 1) & 1u) ^ 1u, 41, prof);
                 ptx::mbar_arrive_expect_tx(&bars->cv_full[cvb], CV_BYTES);
-                ptx::tma_load_1d(smem + SMEM_CV + cvb * CV_BYTES, prm.table + (tile / prm.nseg) * CV_FLOATS, CV_BYTES, &bars->cv_full[cvb]);
+                ptx::tma_load_1d(smem + SMEM_CV + cvb * CV_BYTES, prm.table + (tile / prm.nseg) * CV_ROW_FLOATS, CV_BYTES, &bars->cv_full[cvb]);
                 const uint8_t *src = prm.weights;
                 for (int b = 0; b < 2 * BLOCKS_PER_MLP; ++b) {
                     const uint32_t bytes = (b % BLOCKS_PER_MLP) < 40 ? W_BLK_BYTES : W128_BLK_BYTES;
@@ -394,8 +383,7 @@ constexpr int TB_SMEM_F = 0;
 constexpr int TB_SMEM_W = 5 * A_BLK_BYTES;
 constexpr int TB_SMEM_BAR = TB_SMEM_W + TB_NSTAGE * W_BLK_BYTES;
 constexpr int TB_SMEM_TOTAL = TB_SMEM_BAR + 256 + 1024;
-constexpr int TB_CHUNKS = 12;                            // per MLP: 4 x layer 0, layer 2, layer 3 (+ layer 4 row)
-constexpr size_t TB_MLP_BYTES = (size_t)25 * W_BLK_BYTES + 5 * (size_t)W3_BLK_BYTES;
+constexpr int TB_CHUNKS = 2 * TB_CHUNKS_PER_MLP;
 
 struct TbBars {
     uint64_t full_w[TB_NSTAGE], empty_w[TB_NSTAGE];
@@ -407,6 +395,7 @@ struct TbBars {
 struct TbParams {
     const uint8_t *weights;        // 2 x TB_MLP_BYTES
     const float *bias[2][SURS_NUM_LAYERS];
+    const float *g0;               // [2][512]: bias of the C1 block
     FeatMaps fm;
     float *table;
     int64_t ncols;
@@ -448,16 +437,19 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&bars->f_ready);
-            float *dst_col = prm.table + col * CV_FLOATS;
+            float *dst_col = prm.table + col * CV_ROW_FLOATS;
 #pragma unroll 1
             for (int ch = 0; ch < TB_CHUNKS; ++ch) {
-                const int m = ch / 6, cc = ch % 6, t = ch & 1;
+                const int m = ch / TB_CHUNKS_PER_MLP, cc = ch % TB_CHUNKS_PER_MLP, t = ch & 1;
                 ptx::mbar_wait(&bars->acc_full[t], acc[t] & 1u, 70);
                 ptx::tc_fence_after();
                 const uint32_t taddr = tmem + t * 256 + ((uint32_t)(warp * 32) << 16);
-                const int ncols_out = cc < 5 ? 256 : 128;
-                const float *bias = cc < 4 ? prm.bias[m][0] + cc * 256 : (cc == 4 ? prm.bias[m][2] : prm.bias[m][3]);
-                float *dst = dst_col + m * CV_STRIDE + (cc < 4 ? CV_C0 + cc * 256 : (cc == 4 ? CV_C2 : CV_C3));
+                const int ncols_out = cc < 7 ? 256 : 128;
+                const float *bias = cc < 4 ? prm.bias[m][0] + cc * 256
+                                  : cc < 6 ? prm.g0 + m * 512 + (cc - 4) * 256 : (cc == 6 ? prm.bias[m][2] : prm.bias[m][3]);
+                float *dst = cc < 4 ? dst_col + m * CV_STRIDE + CV_C0 + cc * 256
+                           : cc < 6 ? dst_col + CV_C1 + m * 512 + (cc - 4) * 256
+                                    : dst_col + m * CV_STRIDE + (cc == 6 ? CV_C2 : CV_C3);
 #pragma unroll 1
                 for (int c0 = 0; c0 < ncols_out; c0 += 32) {
                     uint32_t r[32];
@@ -473,7 +465,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
                         }
                     }
                 }
-                if (cc == 5) {                                     // column 128 = W4's skip part . f
+                if (cc == 7) {                                     // column 128 = W4's skip part . f
                     uint32_t r[32];
                     ptx::tmem_ld32(taddr + 128, r);
                     ptx::tmem_ld_wait();
@@ -503,7 +495,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
                         ptx::mbar_wait(&bars->full_w[s], (wblk / TB_NSTAGE) & 1u, 73);
                         ptx::tc_fence_after();
                         mma_block(tmem + t * 256, f_smem + kb * A_BLK_BYTES, w_smem + s * W_BLK_BYTES, 4,
-                                  (ch % 6) == 5 ? IDESC144 : IDESC256, kb == 0);
+                                  (ch % TB_CHUNKS_PER_MLP) == 7 ? IDESC144 : IDESC256, kb == 0);
                         ptx::umma_commit(&bars->empty_w[s]);
                         ++wblk;
                     }
@@ -519,7 +511,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
                 const uint8_t *src = prm.weights;
                 for (int ch = 0; ch < TB_CHUNKS; ++ch)
                     for (int kb = 0; kb < 5; ++kb) {
-                        const uint32_t bytes = (ch % 6) == 5 ? W3_BLK_BYTES : W_BLK_BYTES;
+                        const uint32_t bytes = (ch % TB_CHUNKS_PER_MLP) == 7 ? W3_BLK_BYTES : W_BLK_BYTES;
                         const uint32_t s = wblk % TB_NSTAGE;
                         ptx::mbar_wait(&bars->empty_w[s], ((wblk / TB_NSTAGE) & 1u) ^ 1u, 74);
                         ptx::mbar_arrive_expect_tx(&bars->full_w[s], bytes);
@@ -568,30 +560,98 @@ __global__ void build_gv_kernel(GvSrc s0, GvSrc s1, float *gv)
     }
 }
 
+
+// G = 0.01 W1 W0 (512 x cin0): layer 1 applied to the negative-slope branch of layer 0, plus its
+// constant part g0 = 0.01 W1 b0 + b1 and the columns of G that multiply z_feat / pred_lr.
+struct GSrc {
+    const float *w0t, *w1t;        // transposed fp32: [cin0][1024], [1024][512]
+    const float *b0, *b1;
+    int cin0;
+};
+__global__ void build_g_kernel(GSrc s0, GSrc s1, float *G, float *g0, float *qstar, float *rstar)
+{
+    const int m = blockIdx.y, n = blockIdx.x;
+    const GSrc &s = m == 0 ? s0 : s1;
+    const int j = threadIdx.x;                                   // column of G; j == G_STRIDE: the constant part
+    float acc = 0.0f;
+    if (j < s.cin0)
+        for (int c = 0; c < 1024; ++c) acc = fmaf(s.w1t[(size_t)c * 512 + n], s.w0t[(size_t)j * 1024 + c], acc);
+    else if (j == G_STRIDE)
+        for (int c = 0; c < 1024; ++c) acc = fmaf(s.w1t[(size_t)c * 512 + n], s.b0[c], acc);
+    acc *= SURS_LEAKY;
+    if (j < G_STRIDE) G[((size_t)m * 512 + n) * G_STRIDE + j] = j < s.cin0 ? acc : 0.0f;
+    else g0[m * 512 + n] = acc + s.b1[n];
+    if (j == 320) qstar[m * 512 + n] = acc;
+    if (j == 321) rstar[m * 512 + n] = j < s.cin0 ? acc : 0.0f;
+}
+
+__global__ void build_w1h_kernel(const float *w1t_lr, const float *w1t_hr, __half *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;         // 2 x 1024 x 512
+    if (i < 2 * 1024 * 512) out[i] = __float2half_rn(i < 1024 * 512 ? w1t_lr[i] : w1t_hr[i - 1024 * 512]);
+}
+
+__global__ void build_xv_kernel(GvSrc s0, GvSrc s1, float *xv)
+{
+    const GvSrc &s = blockIdx.x == 0 ? s0 : s1;
+    float *o = xv + blockIdx.x * XV_LR_FLOATS;
+    const bool hp = s.has_pred != 0;
+    for (int c = threadIdx.x; c < 1024; c += blockDim.x) {
+        o[XV_WZ0 + c] = s.w[0][(size_t)c * s.cin[0] + 320];
+        if (hp) o[XV_WP0 + c] = s.w[0][(size_t)c * s.cin[0] + 321];
+    }
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+        o[XV_WZ2 + c] = s.w[2][(size_t)c * s.cin[2] + 512 + 320];
+        if (hp) o[XV_WP2 + c] = s.w[2][(size_t)c * s.cin[2] + 512 + 321];
+    }
+    for (int c = threadIdx.x; c < 128; c += blockDim.x) {
+        o[XV_WZ3 + c] = s.w[3][(size_t)c * s.cin[3] + 256 + 320];
+        if (hp) o[XV_WP3 + c] = s.w[3][(size_t)c * s.cin[3] + 256 + 321];
+        o[XV_W4Y + c] = s.w[4][c];
+    }
+    if (threadIdx.x < 4) {
+        o[XV_WZ4 + threadIdx.x] = threadIdx.x == 0 ? s.w[4][128 + 320] : 0.0f;
+        if (hp) o[XV_WP4 + threadIdx.x] = threadIdx.x == 0 ? s.w[4][128 + 321] : 0.0f;
+    }
+}
+
 }  // namespace
 
 int surs_col_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS], cudaStream_t st)
 {
-    const size_t total = 2 * MLP_BYTES + 2 * TB_MLP_BYTES + GV_BYTES;
-    if (!ctx->col_weights) SURS_CUDA(ctx, cudaMalloc(&ctx->col_weights, total));
+    if (!ctx->col_weights) SURS_CUDA(ctx, cudaMalloc(&ctx->col_weights, COL_WEIGHTS_BYTES));
     uint8_t *base = (uint8_t *)ctx->col_weights;
-    PackDesc host[2 * BLOCKS_PER_MLP + 2 * 30];
+    float *G = reinterpret_cast<float *>(base + OFF_G);
+    GSrc gs[2];
+    for (int m = 0; m < 2; ++m) {
+        gs[m].w0t = ctx->wt32[m][0]; gs[m].w1t = ctx->wt32[m][1];
+        gs[m].b0 = ctx->b32[m][0]; gs[m].b1 = ctx->b32[m][1];
+        gs[m].cin0 = ctx->cin[m][0];
+    }
+    build_g_kernel<<<dim3(512, 2), G_STRIDE + 1, 0, st>>>(gs[0], gs[1], G, reinterpret_cast<float *>(base + OFF_G0),
+                                                         reinterpret_cast<float *>(base + OFF_QSTAR), reinterpret_cast<float *>(base + OFF_RSTAR));
+    SURS_LAUNCH_CHECK(ctx, "build_g_kernel");
+
+    PackDesc host[2 * BLOCKS_PER_MLP + 2 * 40 + 2 * XW_BLOCKS_PER_MLP];
     int n = 0;
     uint32_t off = 0;
-    auto add = [&](int m, int layer, int row0, int nrows, int ntotal, int fblock, int k0, bool extra) {
+    auto add_src = [&](const float *src, int cin, const float *extra, int row0, int nrows, int ntotal, int fblock, int k0, int c0) {
         PackDesc d;
         memset(&d, 0, sizeof(d));
-        d.w = w[m][layer];
-        d.cin = ctx->cin[m][layer];
-        d.w_extra = extra ? w[m][4] : nullptr;
+        d.w = src;
+        d.cin = cin;
+        d.w_extra = extra;
         d.k0_extra = 128;
         d.row0 = row0; d.nrows = nrows; d.ntotal = ntotal; d.fblock = fblock; d.k0 = k0;
-        d.c0 = m == 0 ? SURS_C0_LR : SURS_C0_HR;
+        d.c0 = c0;
         d.out_off = off;
         off += (uint32_t)ntotal * 128u;
         host[n++] = d;
     };
-    for (int m = 0; m < 2; ++m) {                                   // main stream
+    auto add = [&](int m, int layer, int row0, int nrows, int ntotal, int fblock, int k0, bool extra) {
+        add_src(w[m][layer], ctx->cin[m][layer], extra ? w[m][4] : nullptr, row0, nrows, ntotal, fblock, k0, m == 0 ? SURS_C0_LR : SURS_C0_HR);
+    };
+    for (int m = 0; m < 2; ++m) {                                   // query_col.cu main stream
         for (int kb = 0; kb < 16; ++kb) {
             add(m, 1, 0, 256, 256, -1, kb * 64, false);
             add(m, 1, 256, 256, 256, -1, kb * 64, false);
@@ -599,14 +659,23 @@ int surs_col_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS
         for (int kb = 0; kb < 8; ++kb) add(m, 2, 0, 256, 256, -1, kb * 64, false);
         for (int kb = 0; kb < 4; ++kb) add(m, 3, 0, 128, 128, -1, kb * 64, false);
     }
-    if (off != 2 * MLP_BYTES) SURS_FAIL(ctx, "internal: column weight stream size mismatch");
+    if (off != OFF_TABLE) SURS_FAIL(ctx, "internal: column weight stream size mismatch");
     for (int m = 0; m < 2; ++m) {                                   // table stream (image-feature columns only)
         for (int c = 0; c < 4; ++c)
             for (int kb = 0; kb < 5; ++kb) add(m, 0, c * 256, 256, 256, kb, 0, false);
+        for (int c = 0; c < 2; ++c)
+            for (int kb = 0; kb < 5; ++kb) add_src(G + (size_t)m * 512 * G_STRIDE, G_STRIDE, nullptr, c * 256, 256, 256, kb, 0, SURS_C0_LR);
         for (int kb = 0; kb < 5; ++kb) add(m, 2, 0, 256, 256, kb, 512, false);
         for (int kb = 0; kb < 5; ++kb) add(m, 3, 0, 128, W3_ROWS, kb, 256, true);
     }
-    if (off != 2 * MLP_BYTES + 2 * TB_MLP_BYTES) SURS_FAIL(ctx, "internal: table weight stream size mismatch");
+    if (off != OFF_GV) SURS_FAIL(ctx, "internal: table weight stream size mismatch");
+    off = (uint32_t)OFF_XW;
+    for (int m = 0; m < 2; ++m) {                                   // query_inc.cu stream: 128-row blocks
+        for (int kb = 0; kb < 8; ++kb)
+            for (int h = 0; h < 2; ++h) add(m, 2, h * 128, 128, 128, -1, kb * 64, false);
+        for (int kb = 0; kb < 4; ++kb) add(m, 3, 0, 128, 128, -1, kb * 64, false);
+    }
+    if (off != OFF_XV) SURS_FAIL(ctx, "internal: incremental weight stream size mismatch");
     PackDesc *dev = nullptr;
     SURS_CUDA(ctx, cudaMalloc(&dev, sizeof(PackDesc) * n));
     SURS_CUDA(ctx, cudaMemcpyAsync(dev, host, sizeof(PackDesc) * n, cudaMemcpyHostToDevice, st));
@@ -618,25 +687,26 @@ int surs_col_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS
         s[m].b1 = ctx->b32[m][1];
         s[m].has_pred = m;
     }
-    build_gv_kernel<<<2, 256, 0, st>>>(s[0], s[1], reinterpret_cast<float *>(base + 2 * MLP_BYTES + 2 * TB_MLP_BYTES));
+    build_gv_kernel<<<2, 256, 0, st>>>(s[0], s[1], reinterpret_cast<float *>(base + OFF_GV));
     SURS_LAUNCH_CHECK(ctx, "build_gv_kernel");
+    build_xv_kernel<<<2, 256, 0, st>>>(s[0], s[1], reinterpret_cast<float *>(base + OFF_XV));
+    SURS_LAUNCH_CHECK(ctx, "build_xv_kernel");
+    build_w1h_kernel<<<2 * 1024 * 512 / 256, 256, 0, st>>>(ctx->wt32[0][1], ctx->wt32[1][1], reinterpret_cast<__half *>(base + OFF_W1H));
+    SURS_LAUNCH_CHECK(ctx, "build_w1h_kernel");
     SURS_CUDA(ctx, cudaStreamSynchronize(st));
     SURS_CUDA(ctx, cudaFree(dev));
     return 0;
 }
 
-// Dense slab evaluation through the column-factored kernels.  io: grid mode, lin_base / n / out_* set
-// for planes [plane_lo, plane_lo + nplanes) of a [R0, R1, R2] grid without transform.
-int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st)
+int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo, int64_t ncols, cudaStream_t st)
 {
-    const int64_t ncols = (int64_t)nplanes * R1;
-    if (ncols <= 0) return 0;
-    if (surs_ensure(ctx, (void **)&ctx->col_table, &ctx->col_table_cap, (size_t)ncols * CV_BYTES)) return 1;
+    if (surs_ensure(ctx, (void **)&ctx->col_table, &ctx->col_table_cap, (size_t)ncols * CV_ROW_BYTES)) return 1;
     uint8_t *base = (uint8_t *)ctx->col_weights;
     TbParams tb;
-    tb.weights = base + 2 * MLP_BYTES;
+    tb.weights = base + OFF_TABLE;
     for (int m = 0; m < 2; ++m)
         for (int l = 0; l < SURS_NUM_LAYERS; ++l) tb.bias[m][l] = ctx->b32[m][l];
+    tb.g0 = reinterpret_cast<const float *>(base + OFF_G0);
     tb.fm.f_lr = ctx->f_lr16; tb.fm.f_hr = ctx->f_hr16;
     tb.fm.H_lr = ctx->H_lr; tb.fm.W_lr = ctx->W_lr; tb.fm.H_hr = ctx->H_hr; tb.fm.W_hr = ctx->W_hr;
     tb.table = (float *)ctx->col_table;
@@ -646,10 +716,21 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
     SURS_CUDA(ctx, cudaFuncSetAttribute(col_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
     col_table_kernel<<<tb_grid, TB_THREADS, TB_SMEM_TOTAL, st>>>(io, tb);
     SURS_LAUNCH_CHECK(ctx, "col_table_kernel");
+    return 0;
+}
+
+// Dense slab evaluation through the column-factored kernels.  io: grid mode, lin_base / n / out_* set
+// for planes [plane_lo, plane_lo + nplanes) of a [R0, R1, R2] grid without transform.
+int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st)
+{
+    const int64_t ncols = (int64_t)nplanes * R1;
+    if (ncols <= 0) return 0;
+    if (surs_col_build_table(ctx, io, R1, plane_lo, ncols, st)) return 1;
+    uint8_t *base = (uint8_t *)ctx->col_weights;
 
     ColParams prm;
-    prm.weights = base;
-    prm.gv = reinterpret_cast<const float *>(base + 2 * MLP_BYTES + 2 * TB_MLP_BYTES);
+    prm.weights = base + OFF_MAIN;
+    prm.gv = reinterpret_cast<const float *>(base + OFF_GV);
     prm.table = (const float *)ctx->col_table;
     prm.nseg = (R2 + TILE_M - 1) / TILE_M;
     prm.ntiles = ncols * prm.nseg;

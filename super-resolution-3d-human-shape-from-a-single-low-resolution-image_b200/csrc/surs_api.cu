@@ -300,8 +300,12 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
     io.out_lr = sdf_lr;
     // column-factored path: (u,v) must not depend on the grid's last axis (see query_col.cu)
     static const bool no_column = getenv("SURS_NO_COLUMN") != nullptr;
+    // SURS_COL_INC=1: layer 1 by incremental updates along the column (query_inc.cu; exact but, as measured,
+    // slower than the GEMM of query_col.cu -- experiments/README.md).  Read per call so that tests can toggle it.
+    const bool col_inc = getenv("SURS_COL_INC") != nullptr;
     if (precision == SURS_PREC_FP16 && !transform && calib[2] == 0.0f && calib[6] == 0.0f && res[2] >= 64 && !no_column)
-        return surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st);
+        return col_inc ? surs_launch_query_inc(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st)
+                       : surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st);
     // one launch handles < 2^31 CTAs; split very large slabs
     const int64_t chunk = (int64_t)1 << 30;
     for (int64_t s = 0; s < io.n; s += chunk) {

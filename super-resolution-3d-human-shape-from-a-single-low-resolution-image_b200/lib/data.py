@@ -18,7 +18,7 @@ def _first_existing(folder, stem, exts):
 
 def to_tensor(img):
     """PIL image -> float tensor [C,H,W] in [0,1] (what torchvision's ToTensor does for uint8 images)."""
-    a = np.asarray(img, dtype=np.uint8)
+    a = np.array(img, dtype=np.uint8)
     if a.ndim == 2:
         a = a[:, :, None]
     return torch.from_numpy(np.ascontiguousarray(a.transpose(2, 0, 1))).float().div(255)

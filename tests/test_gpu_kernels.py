@@ -274,3 +274,25 @@ def test_column_factored_dense_path(ctx, case32):
         if res[0] >= 5:
             slab = ctx.eval_grid(*args, precision=_capi.PREC_FP16, plane_lo=1, plane_hi=4)
             assert torch.equal(col[0][1:4], slab[0]) and torch.equal(col[1][1:4], slab[1])
+
+
+def test_incremental_layer1_dense_path(ctx, case32, monkeypatch):
+    """SURS_COL_INC=1: layer 1 updated incrementally along the column (query_inc.cu) instead of as a
+    GEMM -- same occupancies within the fp16 tolerance, deterministic, slabs bit identical."""
+    from surs_b200 import _capi
+    for res, bmax in (((6, 7, 300), [0.5, 0.4, 0.55]), ((4, 33, 128), [0.2, 0.5, 0.5]), ((2, 3, 64), [0.5, 0.5, 0.5])):
+        args = (res, [-0.5] * 3, bmax, case32.calib) + znum(case32)
+        gemm = ctx.eval_grid(*args, precision=_capi.PREC_FP16)
+        ref = ctx.eval_grid(*args, precision=_capi.PREC_FP32)
+        monkeypatch.setenv("SURS_COL_INC", "1")
+        inc = ctx.eval_grid(*args, precision=_capi.PREC_FP16)
+        inc2 = ctx.eval_grid(*args, precision=_capi.PREC_FP16)
+        slab = ctx.eval_grid(*args, precision=_capi.PREC_FP16, plane_lo=1, plane_hi=2)
+        monkeypatch.delenv("SURS_COL_INC")
+        for a, a2, b, g, sl in zip(inc, inc2, ref, gemm, slab):
+            d = (a - b).abs()
+            print("incremental path %s: max|d| vs fp32 %.3g mean %.3g; vs gemm kernel %.3g" %
+                  (res, d.max().item(), d.mean().item(), (a - g).abs().max().item()))
+            assert d.max().item() < TOL_FP16_MAX and d.mean().item() < TOL_FP16_MEAN
+            assert torch.equal(a, a2) and torch.equal(a[1:2], sl)
+            assert np.array_equal((a == 0).cpu().numpy(), (b == 0).cpu().numpy())
