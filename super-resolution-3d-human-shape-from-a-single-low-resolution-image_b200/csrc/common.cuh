@@ -164,6 +164,10 @@ struct surs_ctx {
     size_t mc_cells_cap;
     void *mc_block_tot;                    // per-block totals, then exclusive prefix (uint2 / uint4)
     size_t mc_block_cap;
+    void *mc_bits;                         // 1 bit per node: value > level (fast path)
+    size_t mc_bits_cap;
+    void *mc_cell_tot;                     // per-block vertex / face totals of the active-cell list, then exclusive prefix
+    size_t mc_cell_tot_cap;
     int32_t *mc_vid;                       // edge -> vertex id map, 3 per node
     size_t mc_vid_cap;
     void *mc_tables;                       // device copy of the case tables

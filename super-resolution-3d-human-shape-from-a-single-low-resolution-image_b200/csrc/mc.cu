@@ -396,122 +396,122 @@ __global__ void mc_seam_export_kernel(McParams p, const int32_t *__restrict__ vi
 }
 
 // ------------------------------------------------------------------------------------------
-// Fast path (R2 % 4 == 0): every thread looks at 4 consecutive cells of a k-row with 4 aligned
-// float4 loads (+ 4 scalars), rejects the all-inside / all-outside case on 20 sign bits, and only
-// surface cells go through classify_vals.  A first pass counts, a second pass writes the compact,
-// scan-ordered list of active cells (with their vertex / face offsets); vertices and faces are
-// then emitted by one thread per ACTIVE cell, so the volume is read twice and never again.
+// Fast path (R2 % 4 == 0).  The volume is streamed from HBM exactly once:
+//   mc_sign_kernel      one warp per node row, 128-byte coalesced loads, __ballot -> 1 bit per node
+//                       (17 MB for 512^3: L2 resident for everything that follows)
+//   mc_bits_kernel      one thread per 32 cells of a k-row: the cell is active iff its 8 corner bits
+//                       differ -- six word loads and a dozen logic ops per 32 cells; pass 1 counts,
+//                       pass 2 writes the scan-ordered list of active cells
+//   mc_cell_kernel      one thread per ACTIVE cell (~2 % of the cells): classification with the
+//                       ambiguity deciders -> vertex / triangle counts, block-relative offsets
+//   mc_list_verts / mc_list_faces   one thread per active cell
 // ------------------------------------------------------------------------------------------
-struct CellRec { uint32_t lin, vbase, fbase, pad; };
+struct CellRec { uint32_t lin, vbase, fbase, pad; };     // vbase / fbase relative to the cell's mc_cell_kernel block
 
-struct Quad {
-    int i, j, k0;
-    int ncell;              // number of valid cells among k0 .. k0+3
-    unsigned bits;          // sign bits: 5 per row, rows (0,0) (0,1) (1,0) (1,1)
-    float v[4][5];
-};
+constexpr int MC_SIGN_WARPS = 8;
 
-__device__ __forceinline__ bool load_quad(const McParams &p, float level, uint32_t q, uint32_t nquad, Quad &Q)
+__global__ void __launch_bounds__(MC_SIGN_WARPS * 32) mc_sign_kernel(const float *__restrict__ vol, float level, int64_t nrows, int R2, int W,
+                                                                      uint32_t *__restrict__ bits)
 {
-    Q.ncell = 0;
-    if (q >= nquad) return false;
-    const uint32_t qrow = (uint32_t)p.R2 >> 2;
-    Q.k0 = (int)(q % qrow) * 4;
-    const uint32_t t = q / qrow;
-    Q.j = (int)(t % (uint32_t)p.R1);
-    Q.i = (int)(t / (uint32_t)p.R1);
-    if (Q.i >= p.R0 - 1 || Q.j >= p.R1 - 1) return false;
-    Q.ncell = min(4, p.R2 - 1 - Q.k0);
-    unsigned bits = 0;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * MC_SIGN_WARPS + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const float *src = vol + row * R2;
+    uint32_t *dst = bits + row * W;
+    for (int w0 = 0; w0 < W; w0 += 16) {
+        float v[16];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const float *row = p.vol + node_lin(p, Q.i + (r >> 1), Q.j + (r & 1), Q.k0);
-        const float4 a = __ldg(reinterpret_cast<const float4 *>(row));
-        Q.v[r][0] = a.x; Q.v[r][1] = a.y; Q.v[r][2] = a.z; Q.v[r][3] = a.w;
-        Q.v[r][4] = Q.k0 + 4 < p.R2 ? __ldg(row + 4) : a.w;
+        for (int u = 0; u < 16; ++u) {
+            const int k = (w0 + u) * 32 + lane;
+            v[u] = (w0 + u < W && k < R2) ? __ldcs(src + k) : level;      // streamed: nothing re-reads the floats from L1
+        }
+        uint32_t mine = 0;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) bits |= (Q.v[r][c] > level ? 1u : 0u) << (5 * r + c);
+        for (int u = 0; u < 16; ++u) {
+            const uint32_t word = __ballot_sync(0xffffffffu, v[u] > level);
+            if (lane == u) mine = word;
+        }
+        if (lane < 16 && w0 + lane < W) dst[w0 + lane] = mine;
     }
-    Q.bits = bits;
-    return bits != 0u && bits != 0xFFFFFu;
 }
 
-// cell t of the quad: corner values in Lewiner order; returns false when the cell has no surface
-__device__ __forceinline__ bool quad_cell(const Quad &Q, int t, float (&val)[8])
+__device__ __forceinline__ void block_scan1(unsigned a, unsigned &excl, unsigned &tot)
 {
-    const unsigned b = Q.bits >> t;
-    const unsigned cas = (b & 1u) | ((b >> 1) & 1u) << 1 | ((b >> 6) & 1u) << 2 | ((b >> 5) & 1u) << 3 |
-                         ((b >> 10) & 1u) << 4 | ((b >> 11) & 1u) << 5 | ((b >> 16) & 1u) << 6 | ((b >> 15) & 1u) << 7;
-    if (cas == 0u || cas == 255u) return false;
-    val[0] = Q.v[0][t]; val[1] = Q.v[0][t + 1]; val[2] = Q.v[1][t + 1]; val[3] = Q.v[1][t];
-    val[4] = Q.v[2][t]; val[5] = Q.v[2][t + 1]; val[6] = Q.v[3][t + 1]; val[7] = Q.v[3][t];
-    return true;
-}
-
-__device__ __forceinline__ void block_scan3(uint3 a, uint3 &excl, uint3 &tot)
-{
-    __shared__ uint3 wsum[MC_THREADS / 32];
+    __shared__ unsigned wsum[MC_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint3 inc = a;
+    unsigned inc = a;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const unsigned x = __shfl_up_sync(0xffffffffu, inc.x, o), y = __shfl_up_sync(0xffffffffu, inc.y, o), z = __shfl_up_sync(0xffffffffu, inc.z, o);
-        if (lane >= o) { inc.x += x; inc.y += y; inc.z += z; }
+        const unsigned x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += x;
     }
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
-    uint3 off = make_uint3(0, 0, 0), sum = make_uint3(0, 0, 0);
+    unsigned off = 0, sum = 0;
 #pragma unroll
     for (int w = 0; w < MC_THREADS / 32; ++w) {
         if (w == warp) off = sum;
-        sum.x += wsum[w].x; sum.y += wsum[w].y; sum.z += wsum[w].z;
+        sum += wsum[w];
     }
-    excl = make_uint3(off.x + inc.x - a.x, off.y + inc.y - a.y, off.z + inc.z - a.z);
+    excl = off + inc - a;
     tot = sum;
     __syncthreads();
 }
 
 template <bool WRITE>
-__global__ void __launch_bounds__(MC_THREADS) mc_quad_kernel(McParams p, float level, uint32_t nquad, uint4 *block_tot,
-                                                             unsigned long long *n_amb, CellRec *cells)
+__global__ void __launch_bounds__(MC_THREADS) mc_bits_kernel(McParams p, const uint32_t *__restrict__ bits, int W, uint32_t nthreads,
+                                                             uint4 *block_tot, CellRec *cells)
 {
-    const uint32_t q = blockIdx.x * MC_THREADS + threadIdx.x;
-    Quad Q;
-    uint3 mine = make_uint3(0, 0, 0);
-    unsigned amb = 0;
-    unsigned nv[4] = {0, 0, 0, 0}, nt[4] = {0, 0, 0, 0};
-    const bool any = load_quad(p, level, q, nquad, Q);
-    if (any) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            float val[8];
-            if (t < Q.ncell && quad_cell(Q, t, val)) {
-                Cell c;
-                classify_vals(p, Q.i, Q.j, Q.k0 + t, val, c);
-                nv[t] = (unsigned)c.nv; nt[t] = (unsigned)c.nt;
-                if (c.nt | c.nv) { mine.x += 1; mine.y += nv[t]; mine.z += nt[t]; }
-                amb += c.ambiguous;
-            }
+    const uint32_t t = blockIdx.x * MC_THREADS + threadIdx.x;
+    uint32_t act = 0, row = 0;
+    int w = 0;
+    if (t < nthreads) {
+        w = (int)(t % (uint32_t)W);
+        row = t / (uint32_t)W;
+        const int j = (int)(row % (uint32_t)p.R1), i = (int)(row / (uint32_t)p.R1);
+        const int nvalid = p.R2 - 1 - 32 * w;                              // cells k = 32 w + b with k + 1 < R2
+        if (i < p.R0 - 1 && j < p.R1 - 1 && nvalid > 0) {
+            const uint32_t *r00 = bits + (size_t)row * W + w, *r01 = r00 + W, *r10 = r00 + (size_t)p.R1 * W, *r11 = r10 + W;
+            const bool more = w + 1 < W;
+            const uint32_t a = __ldg(r00), b = __ldg(r01), c = __ldg(r10), d = __ldg(r11);
+            const uint32_t an = more ? __ldg(r00 + 1) : 0u, bn = more ? __ldg(r01 + 1) : 0u, cn = more ? __ldg(r10 + 1) : 0u,
+                           dn = more ? __ldg(r11 + 1) : 0u;
+            const uint32_t a1 = (a >> 1) | (an << 31), b1 = (b >> 1) | (bn << 31), c1 = (c >> 1) | (cn << 31), d1 = (d >> 1) | (dn << 31);
+            const uint32_t any = a | b | c | d | a1 | b1 | c1 | d1, all = a & b & c & d & a1 & b1 & c1 & d1;
+            act = any & ~all;
+            if (nvalid < 32) act &= (1u << nvalid) - 1u;
         }
     }
-    uint3 excl, tot;
-    block_scan3(mine, excl, tot);
+    unsigned excl, tot;
+    block_scan1((unsigned)__popc(act), excl, tot);
     if (!WRITE) {
-        if (amb) atomicAdd(n_amb, (unsigned long long)amb);
-        if (threadIdx.x == 0) block_tot[blockIdx.x] = make_uint4(tot.x, tot.y, tot.z, 0);
-    } else if (mine.x) {
-        const uint4 pre = block_tot[blockIdx.x];
-        uint32_t a = pre.x + excl.x, vb = pre.y + excl.y, fb = pre.z + excl.z;
-        const uint32_t lin0 = q * 4;
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-            if (nv[t] | nt[t]) {
-                CellRec r;
-                r.lin = lin0 + t; r.vbase = vb; r.fbase = fb; r.pad = 0;
-                cells[a++] = r;
-                vb += nv[t]; fb += nt[t];
-            }
+        if (threadIdx.x == 0) block_tot[blockIdx.x] = make_uint4(tot, 0, 0, 0);
+    } else {
+        uint32_t dst = block_tot[blockIdx.x].x + excl;
+        const uint32_t lin0 = row * (uint32_t)p.R2 + 32u * (uint32_t)w;
+        while (act) {
+            const int bpos = __ffs(act) - 1;
+            act &= act - 1;
+            cells[dst++].lin = lin0 + (uint32_t)bpos;
+        }
     }
+}
+
+__global__ void __launch_bounds__(MC_THREADS) mc_cell_kernel(McParams p, CellRec *cells, uint32_t nact, uint4 *block_tot, unsigned long long *n_amb)
+{
+    const uint32_t a = blockIdx.x * MC_THREADS + threadIdx.x;
+    Cell c;
+    c.nv = 0; c.nt = 0; c.ambiguous = 0;
+    if (a < nact) {
+        int i, j, k;
+        cell_coords(p, (int64_t)cells[a].lin, i, j, k);
+        classify(p, i, j, k, c);
+    }
+    unsigned ev, ef, tv, tf;
+    block_scan2((unsigned)c.nv, (unsigned)c.nt, ev, ef, tv, tf);
+    if (a < nact) { cells[a].vbase = ev; cells[a].fbase = ef; }
+    if (threadIdx.x == 0) block_tot[blockIdx.x] = make_uint4(0, tv, tf, 0);
+    if (c.ambiguous) atomicAdd(n_amb, 1ull);
 }
 
 __global__ void __launch_bounds__(1024) mc_scan_blocks3_kernel(uint4 *block_tot, int64_t nblocks, unsigned long long *totals)
@@ -548,11 +548,13 @@ __global__ void __launch_bounds__(1024) mc_scan_blocks3_kernel(uint4 *block_tot,
     if (threadIdx.x == 0) { totals[0] = carry[1]; totals[1] = carry[2]; totals[2] = carry[0]; }
 }
 
-__global__ void __launch_bounds__(128) mc_list_verts_kernel(McParams p, const CellRec *__restrict__ cells, uint32_t nact, McOut o)
+__global__ void __launch_bounds__(128) mc_list_verts_kernel(McParams p, const CellRec *__restrict__ cells, const uint4 *__restrict__ boff,
+                                                            uint32_t nact, McOut o)
 {
     const uint32_t a = blockIdx.x * 128 + threadIdx.x;
     if (a >= nact) return;
-    const CellRec r = cells[a];
+    CellRec r = cells[a];
+    r.vbase += boff[a / MC_THREADS].y;
     int i, j, k;
     cell_coords(p, (int64_t)r.lin, i, j, k);
     Cell c;
@@ -560,13 +562,15 @@ __global__ void __launch_bounds__(128) mc_list_verts_kernel(McParams p, const Ce
     if (c.nv) emit_cell_verts(p, o, i, j, k, c, (int64_t)r.vbase);
 }
 
-__global__ void __launch_bounds__(128) mc_list_faces_kernel(McParams p, const CellRec *__restrict__ cells, uint32_t nact,
-                                                            const int32_t *__restrict__ vid, const int32_t *__restrict__ seam_in,
+__global__ void __launch_bounds__(128) mc_list_faces_kernel(McParams p, const CellRec *__restrict__ cells, const uint4 *__restrict__ boff,
+                                                            uint32_t nact, const int32_t *__restrict__ vid, const int32_t *__restrict__ seam_in,
                                                             int64_t id_offset, int32_t *__restrict__ faces)
 {
     const uint32_t a = blockIdx.x * 128 + threadIdx.x;
     if (a >= nact) return;
-    const CellRec r = cells[a];
+    CellRec r = cells[a];
+    const uint4 bo = boff[a / MC_THREADS];
+    r.vbase += bo.y; r.fbase += bo.z;
     int i, j, k;
     cell_coords(p, (int64_t)r.lin, i, j, k);
     Cell c;
@@ -637,26 +641,45 @@ extern "C" int surs_mc_count(surs_ctx *ctx, const float *vol, const int res[3], 
     static const bool no_fast = getenv("SURS_MC_SLOW") != nullptr;
     ctx->mc_fast = (res[2] % 4 == 0) && ((uintptr_t)vol % 16 == 0) && !no_fast;
     if (ctx->mc_fast) {
-        const uint32_t nquad = (uint32_t)(nnode / 4);
-        const int64_t nb = ((int64_t)nquad + MC_THREADS - 1) / MC_THREADS;
-        if (surs_ensure(ctx, (void **)&ctx->mc_block_tot, &ctx->mc_block_cap, sizeof(uint4) * (size_t)nb)) return 1;
-        uint4 *bt = reinterpret_cast<uint4 *>(ctx->mc_block_tot);
-        mc_quad_kernel<false><<<(unsigned)nb, MC_THREADS, 0, st>>>(p, level, nquad, bt, ctx->counter + 1, nullptr);
-        SURS_LAUNCH_CHECK(ctx, "mc_quad_kernel<count>");
-        mc_scan_blocks3_kernel<<<1, 1024, 0, st>>>(bt, nb, ctx->counter + 2);
+        const int W = (res[2] + 31) / 32;
+        const int64_t nrows = (int64_t)res[0] * res[1];
+        const int64_t nthr = nrows * W;
+        if (nthr >= ((int64_t)1 << 32) || nnode >= ((int64_t)1 << 32)) SURS_FAIL(ctx, "surs_mc_count: volume too large for 32-bit cell ids");
+        const int64_t nbA = (nthr + MC_THREADS - 1) / MC_THREADS;
+        if (surs_ensure(ctx, (void **)&ctx->mc_bits, &ctx->mc_bits_cap, sizeof(uint32_t) * (size_t)nthr)) return 1;
+        if (surs_ensure(ctx, (void **)&ctx->mc_block_tot, &ctx->mc_block_cap, sizeof(uint4) * (size_t)nbA)) return 1;
+        uint32_t *bits = reinterpret_cast<uint32_t *>(ctx->mc_bits);
+        mc_sign_kernel<<<(unsigned)((nrows + MC_SIGN_WARPS - 1) / MC_SIGN_WARPS), MC_SIGN_WARPS * 32, 0, st>>>(vol, level, nrows, res[2], W, bits);
+        SURS_LAUNCH_CHECK(ctx, "mc_sign_kernel");
+        uint4 *btA = reinterpret_cast<uint4 *>(ctx->mc_block_tot);
+        mc_bits_kernel<false><<<(unsigned)nbA, MC_THREADS, 0, st>>>(p, bits, W, (uint32_t)nthr, btA, nullptr);
+        SURS_LAUNCH_CHECK(ctx, "mc_bits_kernel<count>");
+        mc_scan_blocks3_kernel<<<1, 1024, 0, st>>>(btA, nbA, ctx->counter + 5);       // counter[7] = number of active cells
         SURS_LAUNCH_CHECK(ctx, "mc_scan_blocks3_kernel");
-        unsigned long long host[5];
+        unsigned long long host[8];
         SURS_CUDA(ctx, cudaMemcpyAsync(host, ctx->counter, sizeof(host), cudaMemcpyDeviceToHost, st));
         SURS_CUDA(ctx, cudaStreamSynchronize(st));
-        ctx->mc_nv = (int64_t)host[2];
-        ctx->mc_nf = (int64_t)host[3];
-        ctx->mc_nact = (int64_t)host[4];
-        if (ctx->mc_nv >= ((int64_t)1 << 31) || ctx->mc_nf >= ((int64_t)1 << 31)) SURS_FAIL(ctx, "surs_mc_count: mesh too large for int32 indices");
+        ctx->mc_nact = (int64_t)host[7];
+        ctx->mc_nv = ctx->mc_nf = 0;
+        host[1] = 0;
         if (ctx->mc_nact > 0) {
+            const int64_t nbB = (ctx->mc_nact + MC_THREADS - 1) / MC_THREADS;
             if (surs_ensure(ctx, (void **)&ctx->mc_cells, &ctx->mc_cells_cap, sizeof(CellRec) * (size_t)ctx->mc_nact)) return 1;
-            mc_quad_kernel<true><<<(unsigned)nb, MC_THREADS, 0, st>>>(p, level, nquad, bt, nullptr, reinterpret_cast<CellRec *>(ctx->mc_cells));
-            SURS_LAUNCH_CHECK(ctx, "mc_quad_kernel<compact>");
+            if (surs_ensure(ctx, (void **)&ctx->mc_cell_tot, &ctx->mc_cell_tot_cap, sizeof(uint4) * (size_t)nbB)) return 1;
+            CellRec *cells = reinterpret_cast<CellRec *>(ctx->mc_cells);
+            uint4 *btB = reinterpret_cast<uint4 *>(ctx->mc_cell_tot);
+            mc_bits_kernel<true><<<(unsigned)nbA, MC_THREADS, 0, st>>>(p, bits, W, (uint32_t)nthr, btA, cells);
+            SURS_LAUNCH_CHECK(ctx, "mc_bits_kernel<compact>");
+            mc_cell_kernel<<<(unsigned)nbB, MC_THREADS, 0, st>>>(p, cells, (uint32_t)ctx->mc_nact, btB, ctx->counter + 1);
+            SURS_LAUNCH_CHECK(ctx, "mc_cell_kernel");
+            mc_scan_blocks3_kernel<<<1, 1024, 0, st>>>(btB, nbB, ctx->counter + 2);
+            SURS_LAUNCH_CHECK(ctx, "mc_scan_blocks3_kernel");
+            SURS_CUDA(ctx, cudaMemcpyAsync(host, ctx->counter, sizeof(host), cudaMemcpyDeviceToHost, st));
+            SURS_CUDA(ctx, cudaStreamSynchronize(st));
+            ctx->mc_nv = (int64_t)host[2];
+            ctx->mc_nf = (int64_t)host[3];
         }
+        if (ctx->mc_nv >= ((int64_t)1 << 31) || ctx->mc_nf >= ((int64_t)1 << 31)) SURS_FAIL(ctx, "surs_mc_count: mesh too large for int32 indices");
         if (n_verts) *n_verts = ctx->mc_nv;
         if (n_faces) *n_faces = ctx->mc_nf;
         if (n_ambiguous) *n_ambiguous = (int64_t)host[1];
@@ -704,6 +727,7 @@ extern "C" int surs_mc_emit_verts(surs_ctx *ctx, const double *mat, float *verts
     ctx->mc_id_offset = vert_id_offset;
     if (ctx->mc_nv > 0 && ctx->mc_fast) {
         mc_list_verts_kernel<<<(unsigned)((ctx->mc_nact + 127) / 128), 128, 0, st>>>(p, reinterpret_cast<const CellRec *>(ctx->mc_cells),
+                                                                                     reinterpret_cast<const uint4 *>(ctx->mc_cell_tot),
                                                                                      (uint32_t)ctx->mc_nact, o);
         SURS_LAUNCH_CHECK(ctx, "mc_list_verts_kernel");
     } else if (ctx->mc_nv > 0) {
@@ -731,6 +755,7 @@ extern "C" int surs_mc_emit_faces(surs_ctx *ctx, int32_t *faces, const int32_t *
     McParams p = make_params(ctx);
     if (ctx->mc_nf > 0 && ctx->mc_fast) {
         mc_list_faces_kernel<<<(unsigned)((ctx->mc_nact + 127) / 128), 128, 0, st>>>(p, reinterpret_cast<const CellRec *>(ctx->mc_cells),
+                                                                                     reinterpret_cast<const uint4 *>(ctx->mc_cell_tot),
                                                                                      (uint32_t)ctx->mc_nact, ctx->mc_vid, seam_in,
                                                                                      ctx->mc_id_offset, faces);
         SURS_LAUNCH_CHECK(ctx, "mc_list_faces_kernel");

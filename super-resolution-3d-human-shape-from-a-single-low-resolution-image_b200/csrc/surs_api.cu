@@ -69,7 +69,7 @@ extern "C" void surs_destroy(surs_ctx *ctx)
     cudaFree(ctx->f_lr32); cudaFree(ctx->f_hr32); cudaFree(ctx->f_lr16); cudaFree(ctx->f_hr16);
     cudaFree(ctx->axis_dev); cudaFree(ctx->dirty); cudaFree(ctx->idx_list); cudaFree(ctx->counter);
     cudaFree(ctx->stage_pts); cudaFree(ctx->stage_out);
-    cudaFree(ctx->mc_block_tot); cudaFree(ctx->mc_cells); cudaFree(ctx->mc_vid); cudaFree(ctx->mc_tables);
+    cudaFree(ctx->mc_block_tot); cudaFree(ctx->mc_bits); cudaFree(ctx->mc_cell_tot); cudaFree(ctx->mc_cells); cudaFree(ctx->mc_vid); cudaFree(ctx->mc_tables);
     delete ctx;
 }
 
