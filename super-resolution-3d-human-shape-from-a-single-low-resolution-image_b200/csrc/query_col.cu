@@ -35,7 +35,7 @@ constexpr int NA_SLOT = 3;
 constexpr int BLOCKS_PER_MLP = 32 + 8 + 4;
 constexpr int KBLK_PER_MLP = 16 + 4 + 4 + 4;             // A-ring K blocks per MLP
 constexpr int NEPI = 8;
-constexpr int NTHREADS = (NEPI + 2) * 32;
+constexpr int NTHREADS = (NEPI + 3) * 32;            // + MMA issue, weight stream, second MMA issue
 
 constexpr int SMEM_W = 0;
 constexpr int SMEM_A = SMEM_W + NSTAGE * W_BLK_BYTES;
@@ -51,8 +51,12 @@ struct Bars {
     uint64_t a_ready[NA_SLOT], a_free[NA_SLOT];
     uint64_t acc_full[2], acc_free[2];
     uint64_t cv_full[2], cv_empty[2];
+    // second MMA-issuing thread (T1 half of layer 1): it only ever sees its own fills, so that
+    // its parity waits stay exactly one phase behind (a thread that skips fills loses the count)
+    uint64_t full_wb[NSTAGE], a_ready_b[NA_SLOT], t1_free_b;
     uint32_t tmem_base;
 };
+static_assert(sizeof(Bars) <= 256, "barrier block");
 
 struct ColParams {
     const uint8_t *weights;        // 2 x MLP_BYTES
@@ -61,6 +65,7 @@ struct ColParams {
     int64_t ntiles;
     int nseg;                      // tiles per column = ceil(R2 / 128)
     int R1, R2, plane_lo;
+    int ablate;                    // profiling only (SURS_COL_ABLATE): 1 = no weight traffic (results are garbage)
 };
 
 // 32 consecutive channels of one row -> fp16 -> A ring slot.  v = acc + add + wz * zf + wp * pred.
@@ -96,6 +101,37 @@ __device__ __forceinline__ void finish32(const uint32_t *acc, const float *add, 
     }
 }
 
+// Layer 0 for 8 channels (one 16-byte chunk) of 4 rows per lane: the per-channel constants are
+// loaded once for the four rows.  y0 = leaky(C0 + w_z z (+ w_p pred_lr)).
+template <bool HAS_P>
+__device__ __forceinline__ void produce8(const float *c0, const float *wz, const float *wp, const float (&zf)[4], const float (&pred)[4],
+                                         uint32_t dst, int lane, int chunk)
+{
+    float a[8], z[8], p[8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float4 av = *reinterpret_cast<const float4 *>(c0 + 4 * q), zv = *reinterpret_cast<const float4 *>(wz + 4 * q);
+        a[4 * q] = av.x; a[4 * q + 1] = av.y; a[4 * q + 2] = av.z; a[4 * q + 3] = av.w;
+        z[4 * q] = zv.x; z[4 * q + 1] = zv.y; z[4 * q + 2] = zv.z; z[4 * q + 3] = zv.w;
+        if (HAS_P) {
+            const float4 pv = *reinterpret_cast<const float4 *>(wp + 4 * q);
+            p[4 * q] = pv.x; p[4 * q + 1] = pv.y; p[4 * q + 2] = pv.z; p[4 * q + 3] = pv.w;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[i] = fmaf(z[i], zf[r], a[i]);
+            if (HAS_P) v[i] = fmaf(p[i], pred[r], v[i]);
+        }
+        const uint4 o = make_uint4(pack_h2(leaky(v[0]), leaky(v[1])), pack_h2(leaky(v[2]), leaky(v[3])),
+                                   pack_h2(leaky(v[4]), leaky(v[5])), pack_h2(leaky(v[6]), leaky(v[7])));
+        st_shared_v4(dst + sw128_off(lane + 32 * r, chunk), o);
+    }
+}
+
 struct EpiCtx {
     Bars *bars;
     uint32_t a_smem;
@@ -111,11 +147,14 @@ __device__ __forceinline__ uint32_t ring_acquire(EpiCtx &e)
     ptx::mbar_wait(&e.bars->a_free[slot], ((e.g / NA_SLOT) & 1u) ^ 1u, 10, e.prof);
     return slot;
 }
-__device__ __forceinline__ void ring_publish(EpiCtx &e, uint32_t slot)
+__device__ __forceinline__ void ring_publish(EpiCtx &e, uint32_t slot, bool layer0 = false)
 {
     ptx::fence_proxy_async_smem();
     __syncwarp();
-    if (e.lane == 0) ptx::mbar_arrive(&e.bars->a_ready[slot]);
+    if (e.lane == 0) {
+        ptx::mbar_arrive(&e.bars->a_ready[slot]);
+        if (layer0) ptx::mbar_arrive(&e.bars->a_ready_b[slot]);    // layer-0 blocks feed both halves of layer 1
+    }
     ++e.g;
 }
 
@@ -159,12 +198,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
     float *pred_x = reinterpret_cast<float *>(smem + SMEM_PREDX);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long *prof = nullptr;
-    if (PROF && lane == 0 && (warp == 0 || warp >= NEPI)) prof = g_col_prof;
+    if (PROF && lane == 0 && (warp == 0 || warp == NEPI || warp == NEPI + 1)) prof = g_col_prof;
     const long long t_kernel0 = PROF ? clock64() : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&bars->full_w[s], 1); ptx::mbar_init(&bars->empty_w[s], 1); }
-        for (int k = 0; k < NA_SLOT; ++k) { ptx::mbar_init(&bars->a_ready[k], NEPI); ptx::mbar_init(&bars->a_free[k], 1); }
+        for (int k = 0; k < NA_SLOT; ++k) {
+            ptx::mbar_init(&bars->a_ready[k], NEPI); ptx::mbar_init(&bars->a_ready_b[k], NEPI); ptx::mbar_init(&bars->a_free[k], 2);
+        }
+        for (int s = 0; s < NSTAGE; ++s) ptx::mbar_init(&bars->full_wb[s], 1);
+        ptx::mbar_init(&bars->t1_free_b, NEPI);
         for (int t = 0; t < 2; ++t) {
             ptx::mbar_init(&bars->acc_full[t], 1); ptx::mbar_init(&bars->acc_free[t], NEPI);
             ptx::mbar_init(&bars->cv_full[t], 1); ptx::mbar_init(&bars->cv_empty[t], NEPI);
@@ -197,6 +240,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
             const int i = prm.plane_lo + (int)(col / prm.R1), j = (int)(col % prm.R1);
             const Projected pr = project_point(io, (float)io.axis[0][i], (float)io.axis[1][j], (float)io.axis[2][kc]);
             e.zf = pr.zf;
+            float zf4[4], pred4[4] = {0.0f, 0.0f, 0.0f, 0.0f};      // layer 0 works on rows lane + 32 r
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int kr = seg * TILE_M + lane + 32 * r;
+                zf4[r] = project_point(io, (float)io.axis[0][i], (float)io.axis[1][j], (float)io.axis[2][kr < prm.R2 ? kr : prm.R2 - 1]).zf;
+            }
             float pred_lr = 0.0f;
             const uint32_t cvb = it & 1u;
             ptx::mbar_wait(&bars->cv_full[cvb], (it >> 1) & 1u, 11, prof);
@@ -209,11 +258,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
 #pragma unroll 1
                 for (int kb = 0; kb < 16; ++kb) {
                     const uint32_t slot = ring_acquire(e);
-                    const int c = kb * 64 + e.hsel * 32;
+                    const int c = kb * 64 + warp * 8;                    // warp w fills 16-byte chunk w of all 128 rows
                     const uint32_t dst = a_smem + slot * A_BLK_BYTES;
-                    if (m == 0) finish32<false, true, false>(nullptr, cvm + CV_C0 + c, gvm + GV_WZ0 + c, nullptr, e.zf, 0.f, dst, e.row, e.hsel);
-                    else finish32<false, true, true>(nullptr, cvm + CV_C0 + c, gvm + GV_WZ0 + c, gvm + GV_WP0 + c, e.zf, e.pred, dst, e.row, e.hsel);
-                    ring_publish(e, slot);
+                    if (m == 0) produce8<false>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, nullptr, zf4, pred4, dst, lane, warp);
+                    else produce8<true>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, gvm + GV_WP0 + c, zf4, pred4, dst, lane, warp);
+                    ring_publish(e, slot, true);
                 }
                 // E1: layer 1, both halves (bias b1) -> A ring
                 ptx::mbar_wait(&bars->acc_full[0], acc0 & 1u, 20, prof);
@@ -242,17 +291,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                         ptx::tmem_ld32(lane_t1 + q * 32, r);
                         ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) {
-                            const int c = q * 32 + jj;
-                            float v = __uint_as_float(r[jj]) + cvm[CV_C3 + c] + gvm[GV_WZ3 + c] * e.zf;
-                            if (m == 1) v = fmaf(gvm[GV_WP3 + c], e.pred, v);
-                            logit = fmaf(gvm[GV_W4Y + c], leaky(v), logit);
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const int c = q * 32 + 4 * j4;
+                            const float4 a = *reinterpret_cast<const float4 *>(cvm + CV_C3 + c), z = *reinterpret_cast<const float4 *>(gvm + GV_WZ3 + c);
+                            const float4 w4 = *reinterpret_cast<const float4 *>(gvm + GV_W4Y + c);
+                            float v0 = __uint_as_float(r[4 * j4]) + a.x + z.x * e.zf, v1 = __uint_as_float(r[4 * j4 + 1]) + a.y + z.y * e.zf;
+                            float v2 = __uint_as_float(r[4 * j4 + 2]) + a.z + z.z * e.zf, v3 = __uint_as_float(r[4 * j4 + 3]) + a.w + z.w * e.zf;
+                            if (m == 1) {
+                                const float4 p = *reinterpret_cast<const float4 *>(gvm + GV_WP3 + c);
+                                v0 = fmaf(p.x, e.pred, v0); v1 = fmaf(p.y, e.pred, v1); v2 = fmaf(p.z, e.pred, v2); v3 = fmaf(p.w, e.pred, v3);
+                            }
+                            logit = fmaf(w4.x, leaky(v0), logit); logit = fmaf(w4.y, leaky(v1), logit);
+                            logit = fmaf(w4.z, leaky(v2), logit); logit = fmaf(w4.w, leaky(v3), logit);
                         }
                     }
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&bars->acc_free[1]);
+                if (lane == 0) { ptx::mbar_arrive(&bars->acc_free[1]); ptx::mbar_arrive(&bars->t1_free_b); }
                 ++acc1;
                 if (e.hsel == 0) {
                     const float pred = pr.mask * (1.0f / (1.0f + expf(-logit)));
@@ -265,10 +321,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                         io.out_lr[n] = pred_lr;
                     }
                 }
-                // the HR pass of rows 32q.. in warp q + 4 needs the pred_lr computed by warp q
+                // the HR pass needs the pred_lr of rows lane + 32 r (layer 0) and of the warp's own row
                 if (m == 0) {
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-                    if (e.hsel == 1) pred_lr = pred_x[e.row];
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    pred_lr = pred_x[e.row];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) pred4[r] = pred_x[lane + 32 * r];
                 }
             }
             __syncwarp();
@@ -276,13 +334,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
         }
     } else if (warp == NEPI) {
         // =============================== MMA issue ========================================
+        // Every wait / commit of an issuing thread is ~100 cycles of serial latency -- with three waits,
+        // three commits and eight MMAs per K block one thread needs ~1.7 kcycles where the tensor pipe
+        // needs 1024.  So layer 1 is issued by two threads: this one the T0 half (even weight blocks)
+        // plus layers 2 and 3, warp NEPI + 2 the T1 half (odd weight blocks).
         if (lane == 0) {
             constexpr uint32_t IDESC256 = ptx::umma_idesc_f16(128, 256);
             constexpr uint32_t IDESC128 = ptx::umma_idesc_f16(128, 128);
-            uint32_t wblk = 0, ablk = 0, acc0 = 0, acc1 = 0;
+            uint32_t wblk = 0, ablk = 0, acc0 = 0, acc1 = 0, wph = 0;     // wph: per-slot phase of full_w (this thread's fills only)
             auto wait_w = [&]() -> uint32_t {
                 const uint32_t s = wblk % NSTAGE;
-                ptx::mbar_wait(&bars->full_w[s], (wblk / NSTAGE) & 1u, 30, prof);
+                ptx::mbar_wait(&bars->full_w[s], (wph >> s) & 1u, 30, prof);
+                wph ^= 1u << s;
                 ptx::tc_fence_after();
                 return w_smem + s * W_BLK_BYTES;
             };
@@ -296,29 +359,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 ptx::tc_fence_after();
                 return slot;
             };
-            auto release_a = [&](uint32_t slot) {
-                ptx::umma_commit(&bars->a_free[slot]);
+            auto release_a = [&](uint32_t slot, int commits) {
+                for (int c = 0; c < commits; ++c) ptx::umma_commit(&bars->a_free[slot]);
                 ++ablk;
             };
             for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
                 for (int m = 0; m < 2; ++m) {
-                    // layer 1: K = 1024 (16 blocks), N = 512 -> T0 | T1
+                    long long tp = PROF ? clock64() : 0;
+                    auto phase = [&](int slot) {
+                        if (PROF) {
+                            const long long t1 = clock64();
+                            atomicAdd(g_col_prof + slot, (unsigned long long)(t1 - tp));
+                            tp = t1;
+                        }
+                    };
+                    // layer 1, T0 half: K = 1024 (16 blocks), N = 256
                     ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 33, prof);
-                    ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 34, prof);
+                    ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 34, prof);    // keeps this thread's phase count of acc_free[1]
                     ptx::tc_fence_after();
                     for (int kb = 0; kb < 16; ++kb) {
                         const uint32_t slot = wait_a();
-                        uint32_t w = wait_w();
+                        const uint32_t w = wait_w();
                         mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
                         release_w();
-                        w = wait_w();
-                        mma_block(T1, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
-                        release_w();
-                        release_a(slot);
+                        ++wblk;                                   // the odd block belongs to the other thread
+                        release_a(slot, 1);
                     }
                     ptx::umma_commit(&bars->acc_full[0]);
-                    ptx::umma_commit(&bars->acc_full[1]);
                     ++acc0; ++acc1;
+                    phase(50);
                     // layer 2: K = 512 (y1 halves from E1), N = 256 -> T0
                     ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 35, prof);
                     ptx::tc_fence_after();
@@ -327,10 +396,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                         const uint32_t w = wait_w();
                         mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
                         release_w();
-                        release_a(slot);
+                        release_a(slot, 2);
                     }
                     ptx::umma_commit(&bars->acc_full[0]);
                     ++acc0;
+                    phase(51);
                     // layer 3: K = 256, N = 128 -> T1
                     ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 36, prof);
                     ptx::tc_fence_after();
@@ -339,10 +409,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                         const uint32_t w = wait_w();
                         mma_block(T1, a_smem + slot * A_BLK_BYTES, w, 4, IDESC128, kb == 0);
                         release_w();
-                        release_a(slot);
+                        release_a(slot, 2);
                     }
                     ptx::umma_commit(&bars->acc_full[1]);
                     ++acc1;
+                    phase(52);
+                }
+            }
+        }
+    } else if (warp == NEPI + 2) {
+        // =============================== MMA issue, T1 half of layer 1 ======================
+        if (lane == 0) {
+            constexpr uint32_t IDESC256 = ptx::umma_idesc_f16(128, 256);
+            uint32_t wblk = 1, ablk = 0, wph = 0, aph = 0, tph = 0;
+            for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+                for (int m = 0; m < 2; ++m) {
+                    ptx::mbar_wait(&bars->t1_free_b, tph ^ 1u, 37, nullptr);          // E3 of the previous pass has read T1
+                    tph ^= 1u;
+                    ptx::tc_fence_after();
+                    for (int kb = 0; kb < 16; ++kb) {
+                        const uint32_t slot = ablk % NA_SLOT, s = wblk % NSTAGE;
+                        ptx::mbar_wait(&bars->a_ready_b[slot], (aph >> slot) & 1u, 38, nullptr);
+                        aph ^= 1u << slot;
+                        ptx::mbar_wait(&bars->full_wb[s], (wph >> s) & 1u, 39, nullptr);
+                        wph ^= 1u << s;
+                        ptx::tc_fence_after();
+                        mma_block(T1, a_smem + slot * A_BLK_BYTES, w_smem + s * W_BLK_BYTES, 4, IDESC256, kb == 0);
+                        ptx::umma_commit(&bars->empty_w[s]);
+                        ptx::umma_commit(&bars->a_free[slot]);
+                        wblk += 2;
+                        ++ablk;
+                    }
+                    ptx::umma_commit(&bars->acc_full[1]);
+                    wblk += 12; ablk += 12;                       // layers 2 and 3
                 }
             }
         }
@@ -360,8 +459,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     const uint32_t bytes = (b % BLOCKS_PER_MLP) < 40 ? W_BLK_BYTES : W128_BLK_BYTES;
                     const uint32_t s = wblk % NSTAGE;
                     ptx::mbar_wait(&bars->empty_w[s], ((wblk / NSTAGE) & 1u) ^ 1u, 40, prof);
-                    ptx::mbar_arrive_expect_tx(&bars->full_w[s], bytes);
-                    ptx::tma_load_1d(smem + SMEM_W + s * W_BLK_BYTES, src, bytes, &bars->full_w[s]);
+                    // odd layer-1 blocks go to the second issuing thread
+                    uint64_t *full = ((b % BLOCKS_PER_MLP) < 32 && (b & 1)) ? &bars->full_wb[s] : &bars->full_w[s];
+                    if (PROF && (prm.ablate & 1)) {
+                        ptx::mbar_arrive(full);
+                    } else {
+                        ptx::mbar_arrive_expect_tx(full, bytes);
+                        ptx::tma_load_1d(smem + SMEM_W + s * W_BLK_BYTES, src, bytes, full);
+                    }
                     src += bytes;
                     ++wblk;
                 }
@@ -735,6 +840,7 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
     prm.nseg = (R2 + TILE_M - 1) / TILE_M;
     prm.ntiles = ncols * prm.nseg;
     prm.R1 = R1; prm.R2 = R2; prm.plane_lo = plane_lo;
+    prm.ablate = getenv("SURS_COL_ABLATE") ? atoi(getenv("SURS_COL_ABLATE")) : 0;
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
     static const bool profile = getenv("SURS_TC_PROFILE") != nullptr;
     if (!profile) {
@@ -755,5 +861,6 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
                     "| mma: wait_w %.1f wait_a_ready %.1f wait_acc_free(%.1f %.1f %.1f %.1f) | loader wait_empty %.1f wait_cv_empty %.1f\n",
             (long long)prm.ntiles, grid, h[0] * k, h[11] * k, h[10] * k, h[20] * k, h[21] * k, h[22] * k, h[23] * k,
             h[30] * k, h[31] * k, h[33] * k, h[34] * k, h[35] * k, h[36] * k, h[40] * k, h[41] * k);
+    fprintf(stderr, "[surs col profile] mma warp phases, kcycles/tile (both MLPs): wait acc_free + layer 1 %.1f | layer 2 %.1f | layer 3 %.1f\n", h[50] * k, h[51] * k, h[52] * k);
     return 0;
 }
