@@ -95,8 +95,8 @@ __device__ __forceinline__ void finish32(const uint32_t *acc, const float *add, 
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += __uint_as_float(acc[8 * j + i]);
         }
-        const uint4 o = make_uint4(pack_h2(leaky(v[0]), leaky(v[1])), pack_h2(leaky(v[2]), leaky(v[3])),
-                                   pack_h2(leaky(v[4]), leaky(v[5])), pack_h2(leaky(v[6]), leaky(v[7])));
+        const uint4 o = make_uint4(leaky_h2(v[0], v[1]), leaky_h2(v[2], v[3]),
+                                   leaky_h2(v[4], v[5]), leaky_h2(v[6], v[7]));
         st_shared_v4(dst + sw128_off(row, hsel * 4 + j), o);
     }
 }
@@ -126,8 +126,8 @@ __device__ __forceinline__ void produce8(const float *c0, const float *wz, const
             v[i] = fmaf(z[i], zf[r], a[i]);
             if (HAS_P) v[i] = fmaf(p[i], pred[r], v[i]);
         }
-        const uint4 o = make_uint4(pack_h2(leaky(v[0]), leaky(v[1])), pack_h2(leaky(v[2]), leaky(v[3])),
-                                   pack_h2(leaky(v[4]), leaky(v[5])), pack_h2(leaky(v[6]), leaky(v[7])));
+        const uint4 o = make_uint4(leaky_h2(v[0], v[1]), leaky_h2(v[2], v[3]),
+                                   leaky_h2(v[4], v[5]), leaky_h2(v[6], v[7]));
         st_shared_v4(dst + sw128_off(lane + 32 * r, chunk), o);
     }
 }

@@ -289,7 +289,7 @@ __device__ __forceinline__ void apply_emit(const Smem &s, State &st, const uint3
         const float2 zp = s.zp[kk];
         float v0 = fmaf(st.Q0, zp.x, st.P0), v1 = fmaf(st.Q1, zp.x, st.P1);
         if (M) { v0 = fmaf(st.R0, zp.y, v0); v1 = fmaf(st.R1, zp.y, v1); }
-        const uint32_t h = pack_h2(leaky(v0), leaky(v1));
+        const uint32_t h = leaky_h2(v0, v1);
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(ydst + sw128_off(kk, chunk)), "r"(h) : "memory");
     };
     const int ngroups = (E + EV_GROUP - 1) / EV_GROUP;
@@ -350,8 +350,8 @@ __device__ __forceinline__ void finish32(const uint32_t *acc, const float *add, 
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] += __uint_as_float(acc[8 * j + i]);
-        const uint4 o = make_uint4(pack_h2(leaky(v[0]), leaky(v[1])), pack_h2(leaky(v[2]), leaky(v[3])),
-                                   pack_h2(leaky(v[4]), leaky(v[5])), pack_h2(leaky(v[6]), leaky(v[7])));
+        const uint4 o = make_uint4(leaky_h2(v[0], v[1]), leaky_h2(v[2], v[3]),
+                                   leaky_h2(v[4], v[5]), leaky_h2(v[6], v[7]));
         st_shared_v4(dst + sw128_off(row, chunk0 + j), o);
     }
 }

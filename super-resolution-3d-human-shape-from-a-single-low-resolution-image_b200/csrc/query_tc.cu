@@ -101,10 +101,10 @@ __device__ __forceinline__ void epilogue_256(uint32_t taddr, int row, int hsel, 
         const uint32_t *v = r[kb & 1];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint4 o = make_uint4(pack_h2(leaky(__uint_as_float(v[8 * j + 0])), leaky(__uint_as_float(v[8 * j + 1]))),
-                                       pack_h2(leaky(__uint_as_float(v[8 * j + 2])), leaky(__uint_as_float(v[8 * j + 3]))),
-                                       pack_h2(leaky(__uint_as_float(v[8 * j + 4])), leaky(__uint_as_float(v[8 * j + 5]))),
-                                       pack_h2(leaky(__uint_as_float(v[8 * j + 6])), leaky(__uint_as_float(v[8 * j + 7]))));
+            const uint4 o = make_uint4(leaky_h2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])),
+                                       leaky_h2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                       leaky_h2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                       leaky_h2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
             const uint32_t off = sw128_off(row, hsel * 4 + j);
             if (to_smem) st_shared_v4(a_smem + slot * A_BLK_BYTES + off, o);
             else *reinterpret_cast<uint4 *>(dst_gmem + kb * A_BLK_BYTES + off) = o;

@@ -27,6 +27,16 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b)
 
 __device__ __forceinline__ float leaky(float v) { return fmaxf(v, SURS_LEAKY * v); }
 
+// leaky_relu of two fp32 values, rounded to fp16 first: one F2FP + HMUL2 + HMNMX2 for the pair instead of
+// 2 FMUL + 2 FMNMX + F2FP.  The negative side is rounded twice (slope fp16(0.01) = 0.0100021): a relative
+// 2e-4 on values that are 1 % of the scale -- far inside the fp16 operand rounding of the next layer.
+__device__ __forceinline__ uint32_t leaky_h2(float a, float b)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    const __half2 r = __hmax2(h, __hmul2(h, __float2half2_rn(SURS_LEAKY)));
+    return *reinterpret_cast<const uint32_t *>(&r);
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v)
 {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
