@@ -296,3 +296,87 @@ def test_incremental_layer1_dense_path(ctx, case32, monkeypatch):
             assert d.max().item() < TOL_FP16_MAX and d.mean().item() < TOL_FP16_MEAN
             assert torch.equal(a, a2) and torch.equal(a[1:2], sl)
             assert np.array_equal((a == 0).cpu().numpy(), (b == 0).cpu().numpy())
+
+
+def test_marching_cubes_bitmask_word_boundaries(ctx):
+    """Fast path (last axis % 4 == 0): rows that are not a multiple of 32 bits, surfaces crossing word
+    boundaries, a single word per row, and the last cell of a row."""
+    rng = np.random.default_rng(5)
+    for shape in ((6, 7, 36), (5, 9, 100), (4, 4, 4), (3, 5, 64), (7, 3, 132)):
+        vol = rng.random(shape).astype(np.float32)
+        _mc_check(ctx, vol)
+        ramp = np.broadcast_to(np.arange(shape[2], dtype=np.float32) / shape[2], shape).copy()      # one crossing per row ...
+        ramp += 0.3 * rng.random(shape[:2]).astype(np.float32)[:, :, None]                           # ... at a row-dependent k
+        _mc_check(ctx, ramp)
+    edge = np.zeros((3, 3, 64), np.float32)
+    edge[:, :, 31:33] = 1.0                                             # crossings exactly at bits 30|31 and 32|33
+    edge[:, :, 63] = 1.0                                                # and at the last node of the row
+    _mc_check(ctx, edge)
+
+
+def test_transformed_and_short_grids_use_the_generic_kernel(ctx, case32):
+    """A grid transform (lib/sdf.py:10-27) or a short last axis rules out the column kernels;
+    both modes must still agree with the oracle on the same nodes."""
+    from surs_b200 import _capi
+    rot = np.eye(4)
+    a = 0.3
+    rot[:3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]) * 0.9
+    rot[:3, 3] = [0.02, -0.03, 0.01]
+    for res, transform in (((12, 10, 16), None), ((9, 8, 70), rot)):
+        bmin, bmax = np.array([-0.5, -0.45, -0.4]), np.array([0.5, 0.5, 0.45])
+        coords, _ = O.create_grid(*res, bmin, bmax, transform=transform)
+        pts = coords.reshape(3, -1).astype(np.float32)
+        ohr, olr = O.query(pts, case32.calib, case32.feat_lr, case32.feat_hr, case32.mlp_lr, case32.mlp_hr, load_size=case32.load_size)
+        for prec, tol in ((_capi.PREC_FP32, TOL_FP32), (_capi.PREC_FP16, TOL_FP16_MAX)):
+            hr, lr = ctx.eval_grid(res, bmin, bmax, case32.calib, *znum(case32), precision=prec, transform=transform)
+            assert np.abs(hr.cpu().numpy().reshape(-1) - ohr).max() < tol
+            assert np.abs(lr.cpu().numpy().reshape(-1) - olr).max() < tol
+
+
+def test_non_square_feature_maps(ctx):
+    """grid_sample normalises x by W - 1 and y by H - 1 (lib/geometry.py:4-12): maps with H != W."""
+    from surs_b200 import _capi
+    case = syn.SyntheticCase(S=32, seed=3)
+    rng = np.random.default_rng(9)
+    f_lr = rng.standard_normal((256, 6, 11)).astype(np.float32)
+    f_hr = rng.standard_normal((64, 20, 13)).astype(np.float32)
+    c2 = _capi.Context(ctx.device)
+    try:
+        t = lambda a: torch.from_numpy(a).to(c2.device)
+        c2.set_weights([t(w) for w in case.mlp_lr[0]], [t(b) for b in case.mlp_lr[1]], [t(w) for w in case.mlp_hr[0]], [t(b) for b in case.mlp_hr[1]],
+                       syn.MLP_DIM_LR, syn.MLP_DIM_HR, syn.RES_LAYERS)
+        c2.set_features(t(f_lr), t(f_hr))
+        pts = syn.random_points(3000, seed=4, lo=-0.6, hi=0.6)
+        ohr, olr = O.query(pts, case.calib, f_lr, f_hr, case.mlp_lr, case.mlp_hr, load_size=case.load_size)
+        for prec, tol in ((_capi.PREC_FP32, TOL_FP32), (_capi.PREC_FP16, TOL_FP16_MAX)):
+            hr, lr = c2.query(t(pts), case.calib, *znum(case), precision=prec)
+            assert np.abs(hr.cpu().numpy() - ohr).max() < tol and np.abs(lr.cpu().numpy() - olr).max() < tol
+        col = c2.eval_grid((4, 5, 64), [-0.5] * 3, [0.5] * 3, case.calib, *znum(case), precision=_capi.PREC_FP16)
+        ref = c2.eval_grid((4, 5, 64), [-0.5] * 3, [0.5] * 3, case.calib, *znum(case), precision=_capi.PREC_FP32)
+        assert (col[0] - ref[0]).abs().max().item() < TOL_FP16_MAX
+    finally:
+        c2.close()
+
+
+def test_error_paths_report_instead_of_falling_back(case32):
+    """Unsupported configurations fail loudly with a message (no silent CPU / torch fallback in the C ABI)."""
+    from surs_b200 import _capi
+    c2 = _capi.Context("cuda:0")
+    try:
+        t = lambda a: torch.from_numpy(a).to(c2.device)
+        pts = t(syn.random_points(64, seed=1))
+        with pytest.raises(RuntimeError, match="set_weights|weights"):
+            c2.query(pts, case32.calib, *znum(case32))
+        bad = list(syn.MLP_DIM_LR)
+        bad[1] = 512
+        w_lr = [t(w) for w in case32.mlp_lr[0]]
+        with pytest.raises(RuntimeError, match="mlp_dim"):
+            c2.set_weights(w_lr, [t(b) for b in case32.mlp_lr[1]], [t(w) for w in case32.mlp_hr[0]], [t(b) for b in case32.mlp_hr[1]],
+                           bad, syn.MLP_DIM_HR, syn.RES_LAYERS)
+        with pytest.raises(RuntimeError, match="res_layers"):
+            c2.set_weights(w_lr, [t(b) for b in case32.mlp_lr[1]], [t(w) for w in case32.mlp_hr[0]], [t(b) for b in case32.mlp_hr[1]],
+                           syn.MLP_DIM_LR, syn.MLP_DIM_HR, [1, 2, 3])
+        with pytest.raises(RuntimeError, match="2 nodes"):
+            c2.mc_count(torch.zeros((1, 8, 8), device=c2.device), 0.5)
+    finally:
+        c2.close()
