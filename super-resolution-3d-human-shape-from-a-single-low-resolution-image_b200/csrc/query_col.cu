@@ -260,7 +260,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     const uint32_t slot = ring_acquire(e);
                     const int c = kb * 64 + warp * 8;                    // warp w fills 16-byte chunk w of all 128 rows
                     const uint32_t dst = a_smem + slot * A_BLK_BYTES;
-                    if (m == 0) produce8<false>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, nullptr, zf4, pred4, dst, lane, warp);
+                    if (PROF && (prm.ablate & 2)) {
+                        // profiling only: no layer-0 arithmetic (the A block keeps stale data)
+                    } else if (m == 0) produce8<false>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, nullptr, zf4, pred4, dst, lane, warp);
                     else produce8<true>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, gvm + GV_WP0 + c, zf4, pred4, dst, lane, warp);
                     ring_publish(e, slot, true);
                 }
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     for (int kb = 0; kb < 16; ++kb) {
                         const uint32_t slot = wait_a();
                         const uint32_t w = wait_w();
-                        mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
+                        if (!(PROF && (prm.ablate & 4))) mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
                         release_w();
                         ++wblk;                                   // the odd block belongs to the other thread
                         release_a(slot, 1);
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                         ptx::mbar_wait(&bars->full_wb[s], (wph >> s) & 1u, 39, nullptr);
                         wph ^= 1u << s;
                         ptx::tc_fence_after();
-                        mma_block(T1, a_smem + slot * A_BLK_BYTES, w_smem + s * W_BLK_BYTES, 4, IDESC256, kb == 0);
+                        if (!(PROF && (prm.ablate & 4))) mma_block(T1, a_smem + slot * A_BLK_BYTES, w_smem + s * W_BLK_BYTES, 4, IDESC256, kb == 0);
                         ptx::umma_commit(&bars->empty_w[s]);
                         ptx::umma_commit(&bars->a_free[slot]);
                         wblk += 2;
