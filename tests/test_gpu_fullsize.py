@@ -1,0 +1,91 @@
+"""Parity at BASELINE.json's full sizes (512^3 nodes, 512x512 input) through size-independent properties:
+the oracle cannot run 134 M queries, so the tensor-core volume is checked on a random sample of nodes
+against the fp32 mode (itself pinned to the oracle at small sizes), slabs against the whole, the octree
+against the dense volume at the nodes it evaluates, and the meshes through manifoldness."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import surs_oracle as O
+from surs_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP16_MAX = 2e-2          # same stated tolerance as tests/test_gpu_kernels.py
+TOL_FP16_MEAN = 5e-4
+FLIP_BAND = 1e-2
+R = 512
+
+
+@pytest.fixture(scope="module")
+def big():
+    from surs_b200 import _capi
+    ctx = _capi.Context("cuda:0")
+    case = syn.SyntheticCase(S=512, seed=0)
+    t = lambda a: torch.from_numpy(a).to(ctx.device)
+    ctx.set_weights([t(w) for w in case.mlp_lr[0]], [t(b) for b in case.mlp_lr[1]], [t(w) for w in case.mlp_hr[0]], [t(b) for b in case.mlp_hr[1]],
+                    syn.MLP_DIM_LR, syn.MLP_DIM_HR, syn.RES_LAYERS)
+    ctx.set_features(t(case.feat_lr), t(case.feat_hr))
+    zn, zd = float(case.load_size // 2), float(case.z_size)
+    hr, lr = ctx.eval_grid((R, R, R), [-0.5] * 3, [0.5] * 3, case.calib, zn, zd, precision=_capi.PREC_FP16)
+    yield ctx, case, zn, zd, hr, lr
+    ctx.close()
+
+
+def test_dense_512_sample_agrees_with_fp32_mode_and_oracle(big):
+    from surs_b200 import _capi
+    ctx, case, zn, zd, hr, lr = big
+    g = torch.Generator(device=ctx.device).manual_seed(11)
+    idx = torch.randint(0, R ** 3, (400000,), device=ctx.device, generator=g)
+    i, j, k = idx // (R * R), (idx // R) % R, idx % R
+    coords, _ = O.create_grid(R, 1, 1, np.array([-0.5] * 3), np.array([0.5] * 3))       # the reference's axis arithmetic (lib/sdf.py:10-27)
+    ax = torch.from_numpy(np.ascontiguousarray(coords[0, :, 0, 0])).to(ctx.device)      # float64; the same table serves all three axes here
+    pts = torch.stack([ax[i], ax[j], ax[k]]).float().contiguous()
+    ref_hr, ref_lr = ctx.query(pts, case.calib, zn, zd, precision=_capi.PREC_FP32)
+    for a, b in ((hr.reshape(-1)[idx], ref_hr), (lr.reshape(-1)[idx], ref_lr)):
+        d = (a - b).abs()
+        flips = (a > 0.5) != (b > 0.5)
+        print("512^3 sample: max|d| %.3g mean %.3g, %d flips of %d (all within |occ - 0.5| < %g: %s)" %
+              (d.max().item(), d.mean().item(), int(flips.sum()), d.numel(), FLIP_BAND, bool(((b - 0.5).abs()[flips] < FLIP_BAND).all())))
+        assert d.max().item() < TOL_FP16_MAX and d.mean().item() < TOL_FP16_MEAN
+        assert ((b - 0.5).abs()[flips] < FLIP_BAND).all()
+    # a slice of the sample against the CPU oracle itself
+    n = 20000
+    ohr, olr = O.query_chunked(pts[:, :n].cpu().numpy(), case.calib, case.feat_lr, case.feat_hr, case.mlp_lr, case.mlp_hr,
+                               load_size=case.load_size, chunk=10000)
+    assert np.abs(ref_hr[:n].cpu().numpy() - ohr).max() < 2e-5 and np.abs(ref_lr[:n].cpu().numpy() - olr).max() < 2e-5
+
+
+def test_dense_512_slabs_and_repeat_are_bit_identical(big):
+    from surs_b200 import _capi
+    ctx, case, zn, zd, hr, lr = big
+    for lo, hi in ((0, 3), (255, 258), (509, 512)):
+        s_hr, s_lr = ctx.eval_grid((R, R, R), [-0.5] * 3, [0.5] * 3, case.calib, zn, zd, precision=_capi.PREC_FP16, plane_lo=lo, plane_hi=hi)
+        assert torch.equal(s_hr, hr[lo:hi]) and torch.equal(s_lr, lr[lo:hi])
+
+
+def test_dense_512_meshes_are_closed_manifolds(big):
+    ctx, case, zn, zd, hr, lr = big
+    for vol in (hr, lr):
+        v, _, f, _, vals, amb = ctx.marching_cubes(vol, 0.5)
+        v, f = v.cpu().numpy(), f.cpu().numpy()
+        assert f.min() == 0 and f.max() == len(v) - 1
+        assert np.array_equal(np.unique(f), np.arange(len(v)))          # every vertex is used, numbering is dense
+        helpers.mesh_euler_closed(v, f, closed=False)                   # the synthetic surface is cut by the box faces
+        assert v.min() >= 0 and v.max() <= R - 1
+        print("512^3 mesh: %d verts, %d faces, %d ambiguous cells" % (len(v), len(f), amb))
+
+
+def test_octree_512_equals_dense_on_evaluated_nodes(big):
+    """lib/sdf.py:55-120 evaluates a subset of the nodes and fills the rest; where it evaluates, it must see
+    the same occupancy as the dense pass up to the tensor-path tolerance (different kernels: column vs generic)."""
+    from surs_b200 import _capi
+    ctx, case, zn, zd, hr, lr = big
+    o_hr, o_lr, n_eval = ctx.eval_grid_octree((R, R, R), [-0.5] * 3, [0.5] * 3, case.calib, zn, zd, threshold=0.05, init_resolution=64,
+                                               precision=_capi.PREC_FP16)
+    assert 0 < n_eval < R ** 3 // 4
+    coarse = (slice(0, R, 8),) * 3                                      # every node of the stride-8 lattice was evaluated
+    for o, d in ((o_hr, hr), (o_lr, lr)):
+        diff = (o[coarse].float() - d[coarse]).abs()
+        assert diff.max().item() < 2 * TOL_FP16_MAX
