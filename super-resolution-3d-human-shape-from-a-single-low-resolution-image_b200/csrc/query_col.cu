@@ -132,6 +132,48 @@ __device__ __forceinline__ void produce8(const float *c0, const float *wz, const
     }
 }
 
+// Indexed mode (octree lists): the four rows of a lane belong to arbitrary columns, so each row brings its
+// own C0 from the column table (global memory; rows of one column share the cache line).
+struct C0Rows {
+    float4 v[4][2];
+};
+__device__ __forceinline__ void load_c0_rows(C0Rows &c, const float *const (&trow)[4], int off)
+{
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        c.v[r][0] = __ldg(reinterpret_cast<const float4 *>(trow[r] + off));
+        c.v[r][1] = __ldg(reinterpret_cast<const float4 *>(trow[r] + off + 4));
+    }
+}
+template <bool HAS_P>
+__device__ __forceinline__ void produce8x(const C0Rows &c0, const float *wz, const float *wp, const float (&zf)[4], const float (&pred)[4],
+                                          uint32_t dst, int lane, int chunk)
+{
+    float z[8], p[8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float4 zv = *reinterpret_cast<const float4 *>(wz + 4 * q);
+        z[4 * q] = zv.x; z[4 * q + 1] = zv.y; z[4 * q + 2] = zv.z; z[4 * q + 3] = zv.w;
+        if (HAS_P) {
+            const float4 pv = *reinterpret_cast<const float4 *>(wp + 4 * q);
+            p[4 * q] = pv.x; p[4 * q + 1] = pv.y; p[4 * q + 2] = pv.z; p[4 * q + 3] = pv.w;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float a[8] = {c0.v[r][0].x, c0.v[r][0].y, c0.v[r][0].z, c0.v[r][0].w, c0.v[r][1].x, c0.v[r][1].y, c0.v[r][1].z, c0.v[r][1].w};
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[i] = fmaf(z[i], zf[r], a[i]);
+            if (HAS_P) v[i] = fmaf(p[i], pred[r], v[i]);
+        }
+        const uint4 o = make_uint4(leaky_h2(v[0], v[1]), leaky_h2(v[2], v[3]),
+                                   leaky_h2(v[4], v[5]), leaky_h2(v[6], v[7]));
+        st_shared_v4(dst + sw128_off(lane + 32 * r, chunk), o);
+    }
+}
+
 struct EpiCtx {
     Bars *bars;
     uint32_t a_smem;
@@ -184,7 +226,10 @@ __device__ __forceinline__ void epilogue_256(EpiCtx &e, uint32_t taddr, int acc_
 
 __device__ unsigned long long g_col_prof[64];
 
-template <bool PROF>
+// INDEXED: the tile is 128 consecutive entries of io.idx_list (octree levels) instead of 128 consecutive k of
+// one column; column vectors are read per row from the table of ALL columns (plane_lo = 0), results are
+// scattered with pointio_store.
+template <bool PROF, bool INDEXED>
 __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_constant__ PointIO io, const __grid_constant__ ColParams prm)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -233,28 +278,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
         const uint32_t lane_t0 = T0 + ((uint32_t)(quarter * 32) << 16), lane_t1 = T1 + ((uint32_t)(quarter * 32) << 16);
         uint32_t acc0 = 0, acc1 = 0, it = 0;
         for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++it) {
-            const int64_t col = tile / prm.nseg;
-            const int seg = (int)(tile - col * prm.nseg);
-            const int k = seg * TILE_M + e.row;
-            const int kc = k < prm.R2 ? k : prm.R2 - 1;
-            const int i = prm.plane_lo + (int)(col / prm.R1), j = (int)(col % prm.R1);
-            const Projected pr = project_point(io, (float)io.axis[0][i], (float)io.axis[1][j], (float)io.axis[2][kc]);
-            e.zf = pr.zf;
+            int64_t col = 0, n_own = 0;
+            int k = 0;
+            Projected pr;
             float zf4[4], pred4[4] = {0.0f, 0.0f, 0.0f, 0.0f};      // layer 0 works on rows lane + 32 r
+            const float *trow4[4] = {nullptr, nullptr, nullptr, nullptr};
+            const float *cv = nullptr;
+            uint32_t cvb = 0;
+            if (!INDEXED) {
+                col = tile / prm.nseg;
+                const int seg = (int)(tile - col * prm.nseg);
+                k = seg * TILE_M + e.row;
+                const int kc = k < prm.R2 ? k : prm.R2 - 1;
+                const int i = prm.plane_lo + (int)(col / prm.R1), j = (int)(col % prm.R1);
+                pr = project_point(io, (float)io.axis[0][i], (float)io.axis[1][j], (float)io.axis[2][kc]);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int kr = seg * TILE_M + lane + 32 * r;
-                zf4[r] = project_point(io, (float)io.axis[0][i], (float)io.axis[1][j], (float)io.axis[2][kr < prm.R2 ? kr : prm.R2 - 1]).zf;
+                for (int r = 0; r < 4; ++r) {
+                    const int kr = seg * TILE_M + lane + 32 * r;
+                    zf4[r] = project_point(io, (float)io.axis[0][i], (float)io.axis[1][j], (float)io.axis[2][kr < prm.R2 ? kr : prm.R2 - 1]).zf;
+                }
+                cvb = it & 1u;
+                ptx::mbar_wait(&bars->cv_full[cvb], (it >> 1) & 1u, 11, prof);
+                cv = cv_s + cvb * CV_FLOATS;
+            } else {
+                auto node = [&](int64_t n, int64_t &c, Projected &q) {
+                    const int64_t lin = io.idx_list[n < io.n ? n : io.n - 1];
+                    c = lin / prm.R2;
+                    const int kk = (int)(lin - c * prm.R2), jj = (int)(c % prm.R1), ii = (int)(c / prm.R1);
+                    q = project_point(io, (float)io.axis[0][ii], (float)io.axis[1][jj], (float)io.axis[2][kk]);
+                };
+                n_own = tile * TILE_M + e.row;
+                node(n_own, col, pr);
+                cv = prm.table + col * CV_ROW_FLOATS;               // this row's column vectors, in global memory
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    int64_t c;
+                    Projected q;
+                    node(tile * TILE_M + lane + 32 * r, c, q);
+                    zf4[r] = q.zf;
+                    trow4[r] = prm.table + c * CV_ROW_FLOATS;
+                }
             }
+            e.zf = pr.zf;
             float pred_lr = 0.0f;
-            const uint32_t cvb = it & 1u;
-            ptx::mbar_wait(&bars->cv_full[cvb], (it >> 1) & 1u, 11, prof);
-            const float *cv = cv_s + cvb * CV_FLOATS;
 #pragma unroll 1
             for (int m = 0; m < 2; ++m) {
                 const float *cvm = cv + m * CV_STRIDE, *gvm = gv_s + m * GV_STRIDE;
                 e.pred = pred_lr;
                 // layer 0 on the CUDA cores: 16 K blocks of y0 = leaky(C0 + w_z z (+ w_p pred_lr))
+                C0Rows c0rows;
+                if (INDEXED) load_c0_rows(c0rows, trow4, m * CV_STRIDE + CV_C0 + warp * 8);
 #pragma unroll 1
                 for (int kb = 0; kb < 16; ++kb) {
                     const uint32_t slot = ring_acquire(e);
@@ -262,6 +335,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     const uint32_t dst = a_smem + slot * A_BLK_BYTES;
                     if (PROF && (prm.ablate & 2)) {
                         // profiling only: no layer-0 arithmetic (the A block keeps stale data)
+                    } else if (INDEXED) {
+                        if (m == 0) produce8x<false>(c0rows, gvm + GV_WZ0 + c, nullptr, zf4, pred4, dst, lane, warp);
+                        else produce8x<true>(c0rows, gvm + GV_WZ0 + c, gvm + GV_WP0 + c, zf4, pred4, dst, lane, warp);
+                        if (kb < 15) load_c0_rows(c0rows, trow4, m * CV_STRIDE + CV_C0 + c + 64);   // lands while the next slot is awaited
                     } else if (m == 0) produce8<false>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, nullptr, zf4, pred4, dst, lane, warp);
                     else produce8<true>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, gvm + GV_WP0 + c, zf4, pred4, dst, lane, warp);
                     ring_publish(e, slot, true);
@@ -317,6 +394,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     if (m == 0) {
                         pred_lr = pred;
                         pred_x[e.row] = pred;
+                    } else if (INDEXED) {
+                        if (n_own < io.n) pointio_store(io, n_own, pred, pred_lr);
                     } else if (k < prm.R2) {
                         const int64_t n = col * prm.R2 + k;
                         io.out_hr[n] = pred;
@@ -332,7 +411,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 }
             }
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&bars->cv_empty[cvb]);
+            if (!INDEXED && lane == 0) ptx::mbar_arrive(&bars->cv_empty[cvb]);
         }
     } else if (warp == NEPI) {
         // =============================== MMA issue ========================================
@@ -452,10 +531,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
         if (lane == 0) {
             uint32_t wblk = 0, it = 0;
             for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++it) {
-                const uint32_t cvb = it & 1u;
-                ptx::mbar_wait(&bars->cv_empty[cvb], ((it >> 1) & 1u) ^ 1u, 41, prof);
-                ptx::mbar_arrive_expect_tx(&bars->cv_full[cvb], CV_BYTES);
-                ptx::tma_load_1d(smem + SMEM_CV + cvb * CV_BYTES, prm.table + (tile / prm.nseg) * CV_ROW_FLOATS, CV_BYTES, &bars->cv_full[cvb]);
+                if (!INDEXED) {
+                    const uint32_t cvb = it & 1u;
+                    ptx::mbar_wait(&bars->cv_empty[cvb], ((it >> 1) & 1u) ^ 1u, 41, prof);
+                    ptx::mbar_arrive_expect_tx(&bars->cv_full[cvb], CV_BYTES);
+                    ptx::tma_load_1d(smem + SMEM_CV + cvb * CV_BYTES, prm.table + (tile / prm.nseg) * CV_ROW_FLOATS, CV_BYTES, &bars->cv_full[cvb]);
+                }
                 const uint8_t *src = prm.weights;
                 for (int b = 0; b < 2 * BLOCKS_PER_MLP; ++b) {
                     const uint32_t bytes = (b % BLOCKS_PER_MLP) < 40 ? W_BLK_BYTES : W128_BLK_BYTES;
@@ -846,15 +927,15 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
     static const bool profile = getenv("SURS_TC_PROFILE") != nullptr;
     if (!profile) {
-        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        query_col_kernel<false><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        query_col_kernel<false, false><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
         SURS_LAUNCH_CHECK(ctx, "query_col_kernel");
         return 0;
     }
     unsigned long long zero[64] = {0}, h[64];
     SURS_CUDA(ctx, cudaMemcpyToSymbol(g_col_prof, zero, sizeof(zero)));
-    SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    query_col_kernel<true><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+    SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    query_col_kernel<true, false><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
     SURS_LAUNCH_CHECK(ctx, "query_col_kernel<profile>");
     SURS_CUDA(ctx, cudaStreamSynchronize(st));
     SURS_CUDA(ctx, cudaMemcpyFromSymbol(h, g_col_prof, sizeof(h)));
@@ -864,5 +945,27 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
             (long long)prm.ntiles, grid, h[0] * k, h[11] * k, h[10] * k, h[20] * k, h[21] * k, h[22] * k, h[23] * k,
             h[30] * k, h[31] * k, h[33] * k, h[34] * k, h[35] * k, h[36] * k, h[40] * k, h[41] * k);
     fprintf(stderr, "[surs col profile] mma warp phases, kcycles/tile (both MLPs): wait acc_free + layer 1 %.1f | layer 2 %.1f | layer 3 %.1f\n", h[50] * k, h[51] * k, h[52] * k);
+    return 0;
+}
+
+// Octree levels through the column table: io is in grid mode with idx_list / vol_* set (n selected nodes of a
+// [R0, R1, R2] grid without transform); the table must cover all R0 x R1 columns (surs_col_build_table with
+// plane_lo = 0), built once per reconstruction.
+int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int R2, cudaStream_t st)
+{
+    if (io.n <= 0) return 0;
+    uint8_t *base = (uint8_t *)ctx->col_weights;
+    ColParams prm;
+    prm.weights = base + OFF_MAIN;
+    prm.gv = reinterpret_cast<const float *>(base + OFF_GV);
+    prm.table = (const float *)ctx->col_table;
+    prm.nseg = 1;
+    prm.ntiles = (io.n + TILE_M - 1) / TILE_M;
+    prm.R1 = R1; prm.R2 = R2; prm.plane_lo = 0;
+    prm.ablate = 0;
+    const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
+    SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    query_col_kernel<false, true><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+    SURS_LAUNCH_CHECK(ctx, "query_col_kernel<indexed>");
     return 0;
 }

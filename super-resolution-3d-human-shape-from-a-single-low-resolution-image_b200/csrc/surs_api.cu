@@ -1,6 +1,7 @@
 // C-ABI entry points of libsurs.so (see include/surs.h for the contract and the
 // reference file:line each one replaces).
 #include "common.cuh"
+#include "col_common.cuh"
 
 #include <new>
 #include <stdlib.h>
@@ -366,6 +367,10 @@ extern "C" int surs_eval_grid_octree(surs_ctx *ctx, const int res[3], const doub
     fill_proj(io, calib, z_num, z_den);
     io.vol_hr = sdf_hr;
     io.vol_lr = sdf_lr;
+    // Column-table path (same preconditions as the dense column kernels): every W.f product once per column,
+    // for all levels; the levels then run the indexed variant of query_col_kernel.  SURS_NO_COLUMN=1 disables it.
+    const bool use_table = precision == SURS_PREC_FP16 && !transform && calib[2] == 0.0f && calib[6] == 0.0f && getenv("SURS_NO_COLUMN") == nullptr;
+    if (use_table && surs_col_build_table(ctx, io, res[1], 0, (int64_t)res[0] * res[1], st)) return 1;
     while (reso > 0) {
         const size_t cand = (size_t)((res[0] + reso - 1) / reso) * ((res[1] + reso - 1) / reso) * ((res[2] + reso - 1) / reso);
         if (surs_ensure(ctx, (void **)&ctx->idx_list, &ctx->idx_cap, cand * sizeof(int64_t))) return 1;
@@ -377,7 +382,7 @@ extern "C" int surs_eval_grid_octree(surs_ctx *ctx, const int res[3], const doub
             PointIO part = io;
             part.idx_list = ctx->idx_list + s;
             part.n = (nsel - s < chunk) ? nsel - s : chunk;
-            if (run_query(ctx, part, precision, st)) return 1;
+            if (use_table ? surs_launch_query_col_indexed(ctx, part, res[1], res[2], st) : run_query(ctx, part, precision, st)) return 1;
         }
         if (reso <= 1) break;                                   // lib/sdf.py:79
         if (surs_octree_cells_impl(ctx, res, reso, threshold, sdf_hr, sdf_lr, ctx->dirty, st)) return 1;

@@ -176,10 +176,19 @@ def test_fused_octree_equals_oracle_octree_on_same_occupancies(ctx, case32):
         hr, lr, n_eval = ctx.eval_grid_octree(res, [-0.5] * 3, [0.5] * 3, case32.calib, *znum(case32), threshold=0.05,
                                               init_resolution=16, precision=prec)
 
-        def eval_func(points):
-            p = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float32)).to(ctx.device)
-            a, b = ctx.query(p, case32.calib, *znum(case32), precision=prec)
-            return a.cpu().numpy(), b.cpu().numpy()
+        if prec == _capi.PREC_FP32:
+            def eval_func(points):
+                p = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float32)).to(ctx.device)
+                a, b = ctx.query(p, case32.calib, *znum(case32), precision=prec)
+                return a.cpu().numpy(), b.cpu().numpy()
+        else:
+            # the tensor-core octree runs the indexed variant of the column kernel: node for node it must be
+            # bit-identical to the dense column kernel (same table, same per-row arithmetic)
+            dense = [v.cpu().numpy() for v in ctx.eval_grid(res, [-0.5] * 3, [0.5] * 3, case32.calib, *znum(case32), precision=prec)]
+
+            def eval_func(points):
+                ijk = np.rint((np.asarray(points, dtype=np.float64) + 0.5) * 64).astype(np.int64)
+                return dense[0][ijk[0], ijk[1], ijk[2]], dense[1][ijk[0], ijk[1], ijk[2]]
 
         stats = []
         coords, _ = O.create_grid(*res, np.array([-0.5] * 3), np.array([0.5] * 3))
