@@ -33,7 +33,12 @@ typedef struct surs_ctx surs_ctx;
 /* arithmetic used by the MLP chain */
 enum {
     SURS_PREC_FP32 = 0,   /* CUDA-core fp32 FMA chain; agrees with the reference to ~1e-6     */
-    SURS_PREC_FP16 = 1    /* tcgen05 tensor cores, fp16 operands / fp32 accumulate (default)   */
+    SURS_PREC_FP16 = 1,   /* tcgen05 tensor cores, fp16 operands / fp32 accumulate (default)   */
+    SURS_PREC_FP16X3 = 2  /* tensor cores with split operands: every product as A_hi.W_hi + A_lo.W_hi + A_hi.W_lo
+                           * (fp16 hi/lo pairs, fp32 accumulate), ~1e-5 from the reference at a third of the FP16
+                           * rate.  Column-factored grids only (surs_eval_grid / surs_eval_grid_octree without a
+                           * transform and with calib[0][2] == calib[1][2] == 0); every other point source runs
+                           * the SURS_PREC_FP32 kernel. */
 };
 
 #define SURS_NUM_LAYERS 5

@@ -40,6 +40,9 @@ def main():
     col = ctx.eval_grid((res,) * 3, bmin, bmax, case.calib, zn, zd, precision=_capi.PREC_FP16)
     ref = ctx.eval_grid((res,) * 3, bmin, bmax, case.calib, zn, zd, precision=_capi.PREC_FP32)
     out["dense_grid_column_kernel_vs_fp32_mode"] = {"hr": stats(col[0], ref[0], band), "lr": stats(col[1], ref[1], band)}
+    x3 = ctx.eval_grid((res,) * 3, bmin, bmax, case.calib, zn, zd, precision=_capi.PREC_FP16X3)
+    out["dense_grid_split_operand_x3_vs_fp32_mode(band 1e-4)"] = {"hr": stats(x3[0], ref[0], 1e-4), "lr": stats(x3[1], ref[1], 1e-4)}
+    del x3
     out["occupancy_histogram_hr(10 bins)"] = torch.histc(ref[0], bins=10, min=0, max=1).tolist()
     out["occupancy_histogram_lr(10 bins)"] = torch.histc(ref[1], bins=10, min=0, max=1).tolist()
     pts = torch.rand(3, 1 << 22, device=dev, generator=torch.Generator(device=dev).manual_seed(7)) * 1.1 - 0.55

@@ -51,13 +51,15 @@ def main():
     zn, zd = float(case.load_size // 2), float(case.z_size)
     bmin, bmax = np.array([-0.5] * 3), np.array([0.5] * 3)
 
+    prec = {"fp16": _capi.PREC_FP16, "fp16x3": _capi.PREC_FP16X3, "fp32": _capi.PREC_FP32}[os.environ.get("SURS_PRECISION", "fp16")]
+
     def recon(res, octree):
         mat = bsdf.grid_matrix(res, bmin, bmax)[:3, :4]
         if octree:
-            hr, lr, n_eval = ctx.eval_grid_octree((res,) * 3, bmin, bmax, case.calib, zn, zd, 0.05)
+            hr, lr, n_eval = ctx.eval_grid_octree((res,) * 3, bmin, bmax, case.calib, zn, zd, 0.05, precision=prec)
             vols = (ctx.cast_f64_f32(hr), ctx.cast_f64_f32(lr))
         else:
-            vols = ctx.eval_grid((res,) * 3, bmin, bmax, case.calib, zn, zd)
+            vols = ctx.eval_grid((res,) * 3, bmin, bmax, case.calib, zn, zd, precision=prec)
             n_eval = res ** 3
         meshes = []
         for v in vols:
@@ -70,9 +72,11 @@ def main():
     for name, res, octree in (("C1 dense 128^3", 128, False), ("C2 octree 256^3", 256, True), ("C3 dense 512^3", 512, False),
                               ("C4 octree 512^3", 512, True)):
         ms, (n_eval, meshes) = timed(lambda: recon(res, octree))
-        print(json.dumps({"config": name, "input_side": S, "ms_per_mesh": ms, "grid_nodes": res ** 3, "network_evaluations": n_eval,
+        print(json.dumps({"config": name, "precision": os.environ.get("SURS_PRECISION", "fp16"), "input_side": S, "ms_per_mesh": ms, "grid_nodes": res ** 3, "network_evaluations": n_eval,
                           "evaluated_fraction": n_eval / res ** 3, "grid_nodes_per_s": res ** 3 / ms * 1e3,
                           "evaluations_per_s": n_eval / ms * 1e3, "verts_faces_ambiguous_hr_lr": meshes}))
+    if prec != _capi.PREC_FP16:
+        return
     for lg in (20, 22, 24, 26):
         n = 1 << lg
         pts = torch.rand(3, n, device=dev, generator=torch.Generator(device=dev).manual_seed(lg)) - 0.5

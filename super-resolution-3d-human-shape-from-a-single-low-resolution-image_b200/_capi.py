@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(CSRC, "libsurs.so")
 
 PREC_FP32 = 0
 PREC_FP16 = 1
+PREC_FP16X3 = 2     # split hi/lo fp16 operands on the tensor cores (three MMA passes), column-factored grids
 MC_LOWER_FOREIGN = 1
 
 _P = ctypes.c_void_p

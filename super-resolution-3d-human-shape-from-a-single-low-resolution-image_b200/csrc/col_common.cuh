@@ -52,11 +52,13 @@ constexpr size_t OFF_XW = OFF_RSTAR + 2 * 512 * 4;
 constexpr size_t OFF_XV = OFF_XW + 2 * XW_MLP_BYTES;
 constexpr size_t OFF_W1H = (OFF_XV + XV_BYTES + 255) / 256 * 256;    // fp16 W1^T [2][1024][512] (query_inc.cu events)
 constexpr size_t COL_WEIGHTS_BYTES = OFF_W1H + (size_t)2 * 1024 * 512 * 2;
+constexpr size_t X3_BYTES = 3 * OFF_GV;                  // split-operand copy of the main + table streams (surs_ctx::col_weights_x3)
 static_assert(OFF_XW % 1024 == 0 && OFF_TABLE % 1024 == 0, "operand blocks must stay 1024-byte aligned");
 
 }  // namespace col
 
 // per-column table for planes [plane_lo, plane_lo + ncols / R1) -> ctx->col_table (query_col.cu)
-int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo, int64_t ncols, cudaStream_t st);
-int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int R2, cudaStream_t st);
+// passes: 1 = fp16 operands (SURS_PREC_FP16), 3 = split hi/lo operands (SURS_PREC_FP16X3)
+int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo, int64_t ncols, cudaStream_t st, int passes = 1);
+int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int R2, cudaStream_t st, int passes = 1);
 int surs_launch_query_inc(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st);

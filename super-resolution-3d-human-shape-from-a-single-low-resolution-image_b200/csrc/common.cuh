@@ -133,6 +133,7 @@ struct surs_ctx {
     void *tc_scratch;                      // 64 KB per CTA: first half of layer 1 between passes
     size_t tc_scratch_cap;
     void *col_weights;                     // column-factored dense path: weight streams + constant vectors
+    void *col_weights_x3;                  // split-operand (hi, hi, lo) copy of the main + table weight streams
     void *col_table;                       // per-column vectors (query_col.cu)
     size_t col_table_cap;
     float tc_w4y[2][128];                  // W4[0, 0:128] of both MLPs (host copy, passed as kernel parameter)
@@ -203,7 +204,7 @@ int surs_tc_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS]
 int surs_launch_query_tc(surs_ctx *ctx, const PointIO &io, cudaStream_t st);
 // query_col.cu
 int surs_col_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS], cudaStream_t st);
-int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st);
+int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st, int passes = 1);
 int surs_launch_query_inc(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st);
 // mc.cu
 int surs_mc_init_tables(surs_ctx *ctx);

@@ -24,6 +24,7 @@
 // column half w/4), 8 = MMA issue, 9 = weight stream + per-column vectors (bulk TMA).
 #include "col_common.cuh"
 
+#include <new>
 #include <stdlib.h>
 
 namespace {
@@ -69,9 +70,9 @@ struct ColParams {
 };
 
 // 32 consecutive channels of one row -> fp16 -> A ring slot.  v = acc + add + wz * zf + wp * pred.
-template <bool HAS_ACC, bool HAS_Z, bool HAS_P>
+template <int P, bool HAS_ACC, bool HAS_Z, bool HAS_P>
 __device__ __forceinline__ void finish32(const uint32_t *acc, const float *add, const float *wz, const float *wp,
-                                         float zf, float pred, uint32_t dst, int row, int hsel)
+                                         float zf, float pred, uint32_t dst, int row, int hsel, int part)
 {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -95,17 +96,17 @@ __device__ __forceinline__ void finish32(const uint32_t *acc, const float *add, 
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += __uint_as_float(acc[8 * j + i]);
         }
-        const uint4 o = make_uint4(leaky_h2(v[0], v[1]), leaky_h2(v[2], v[3]),
-                                   leaky_h2(v[4], v[5]), leaky_h2(v[6], v[7]));
+        const uint4 o = make_uint4(act_h2<P>(v[0], v[1], part), act_h2<P>(v[2], v[3], part),
+                                   act_h2<P>(v[4], v[5], part), act_h2<P>(v[6], v[7], part));
         st_shared_v4(dst + sw128_off(row, hsel * 4 + j), o);
     }
 }
 
 // Layer 0 for 8 channels (one 16-byte chunk) of 4 rows per lane: the per-channel constants are
 // loaded once for the four rows.  y0 = leaky(C0 + w_z z (+ w_p pred_lr)).
-template <bool HAS_P>
+template <int P, bool HAS_P>
 __device__ __forceinline__ void produce8(const float *c0, const float *wz, const float *wp, const float (&zf)[4], const float (&pred)[4],
-                                         uint32_t dst, int lane, int chunk)
+                                         uint32_t dst, int lane, int chunk, int part)
 {
     float a[8], z[8], p[8];
 #pragma unroll
@@ -126,8 +127,8 @@ __device__ __forceinline__ void produce8(const float *c0, const float *wz, const
             v[i] = fmaf(z[i], zf[r], a[i]);
             if (HAS_P) v[i] = fmaf(p[i], pred[r], v[i]);
         }
-        const uint4 o = make_uint4(leaky_h2(v[0], v[1]), leaky_h2(v[2], v[3]),
-                                   leaky_h2(v[4], v[5]), leaky_h2(v[6], v[7]));
+        const uint4 o = make_uint4(act_h2<P>(v[0], v[1], part), act_h2<P>(v[2], v[3], part),
+                                   act_h2<P>(v[4], v[5], part), act_h2<P>(v[6], v[7], part));
         st_shared_v4(dst + sw128_off(lane + 32 * r, chunk), o);
     }
 }
@@ -145,9 +146,9 @@ __device__ __forceinline__ void load_c0_rows(C0Rows &c, const float *const (&tro
         c.v[r][1] = __ldg(reinterpret_cast<const float4 *>(trow[r] + off + 4));
     }
 }
-template <bool HAS_P>
+template <int P, bool HAS_P>
 __device__ __forceinline__ void produce8x(const C0Rows &c0, const float *wz, const float *wp, const float (&zf)[4], const float (&pred)[4],
-                                          uint32_t dst, int lane, int chunk)
+                                          uint32_t dst, int lane, int chunk, int part)
 {
     float z[8], p[8];
 #pragma unroll
@@ -168,8 +169,8 @@ __device__ __forceinline__ void produce8x(const C0Rows &c0, const float *wz, con
             v[i] = fmaf(z[i], zf[r], a[i]);
             if (HAS_P) v[i] = fmaf(p[i], pred[r], v[i]);
         }
-        const uint4 o = make_uint4(leaky_h2(v[0], v[1]), leaky_h2(v[2], v[3]),
-                                   leaky_h2(v[4], v[5]), leaky_h2(v[6], v[7]));
+        const uint4 o = make_uint4(act_h2<P>(v[0], v[1], part), act_h2<P>(v[2], v[3], part),
+                                   act_h2<P>(v[4], v[5], part), act_h2<P>(v[6], v[7], part));
         st_shared_v4(dst + sw128_off(lane + 32 * r, chunk), o);
     }
 }
@@ -189,7 +190,7 @@ __device__ __forceinline__ uint32_t ring_acquire(EpiCtx &e)
     ptx::mbar_wait(&e.bars->a_free[slot], ((e.g / NA_SLOT) & 1u) ^ 1u, 10, e.prof);
     return slot;
 }
-__device__ __forceinline__ void ring_publish(EpiCtx &e, uint32_t slot, bool layer0 = false)
+__device__ __forceinline__ void ring_publish(EpiCtx &e, uint32_t slot, bool layer0 = false)   // layer0: the block feeds the second issuing thread too
 {
     ptx::fence_proxy_async_smem();
     __syncwarp();
@@ -202,7 +203,7 @@ __device__ __forceinline__ void ring_publish(EpiCtx &e, uint32_t slot, bool laye
 
 // epilogue of a 256-column accumulator into 4 K blocks of the A ring; the accumulator is handed
 // back (acc_free) as soon as its last column has been read, before the last block is written
-template <bool HAS_Z, bool HAS_P>
+template <int P, bool HAS_Z, bool HAS_P>
 __device__ __forceinline__ void epilogue_256(EpiCtx &e, uint32_t taddr, int acc_id, const float *add, const float *wz, const float *wp)
 {
     uint32_t r[2][32];
@@ -217,10 +218,13 @@ __device__ __forceinline__ void epilogue_256(EpiCtx &e, uint32_t taddr, int acc_
             __syncwarp();
             if (e.lane == 0) ptx::mbar_arrive(&e.bars->acc_free[acc_id]);
         }
-        const uint32_t slot = ring_acquire(e);
         const int c = kb * 64 + e.hsel * 32;
-        finish32<true, HAS_Z, HAS_P>(r[kb & 1], add + c, wz + c, wp + c, e.zf, e.pred, e.a_smem + slot * A_BLK_BYTES, e.row, e.hsel);
-        ring_publish(e, slot);
+#pragma unroll 1
+        for (int part = 0; part < P; ++part) {                 // P = 3: the K block goes out as hi, lo, hi
+            const uint32_t slot = ring_acquire(e);
+            finish32<P, true, HAS_Z, HAS_P>(r[kb & 1], add + c, wz + c, wp + c, e.zf, e.pred, e.a_smem + slot * A_BLK_BYTES, e.row, e.hsel, part);
+            ring_publish(e, slot);
+        }
     }
 }
 
@@ -229,7 +233,14 @@ __device__ unsigned long long g_col_prof[64];
 // INDEXED: the tile is 128 consecutive entries of io.idx_list (octree levels) instead of 128 consecutive k of
 // one column; column vectors are read per row from the table of ALL columns (plane_lo = 0), results are
 // scattered with pointio_store.
-template <bool PROF, bool INDEXED>
+// P = 3 (SURS_PREC_FP16X3): every K block of layers 1-3 is issued three times -- A_hi.W_hi, A_lo.W_hi, A_hi.W_lo --
+// from an A ring that carries (hi, lo, hi) and a weight stream that carries (hi, hi, lo).  The schedule differs
+// from P = 1: an accumulator may only be released after its last column has been read, and with three ring
+// slots per K block E1 could no longer park three K blocks in the ring while layer 2 waits for the accumulator
+// it is reading.  So layer 1 runs as two sequential N halves into T0 (layer 0 is produced twice), layer 2
+// accumulates into T1 behind each half, layer 3 goes to T0 -- the accumulator being drained is never the one the
+// consumer of the drained blocks writes to.  One issuing thread; warp NEPI + 2 idles.
+template <bool PROF, bool INDEXED, int P>
 __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_constant__ PointIO io, const __grid_constant__ ColParams prm)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -327,39 +338,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 e.pred = pred_lr;
                 // layer 0 on the CUDA cores: 16 K blocks of y0 = leaky(C0 + w_z z (+ w_p pred_lr))
                 C0Rows c0rows;
+#pragma unroll 1
+                for (int half = 0; half < (P == 1 ? 1 : 2); ++half) {
                 if (INDEXED) load_c0_rows(c0rows, trow4, m * CV_STRIDE + CV_C0 + warp * 8);
 #pragma unroll 1
-                for (int kb = 0; kb < 16; ++kb) {
+                for (int kp = 0; kp < 16 * P; ++kp) {
+                    const int kb = kp / P, part = kp - kb * P;
                     const uint32_t slot = ring_acquire(e);
                     const int c = kb * 64 + warp * 8;                    // warp w fills 16-byte chunk w of all 128 rows
                     const uint32_t dst = a_smem + slot * A_BLK_BYTES;
                     if (PROF && (prm.ablate & 2)) {
                         // profiling only: no layer-0 arithmetic (the A block keeps stale data)
                     } else if (INDEXED) {
-                        if (m == 0) produce8x<false>(c0rows, gvm + GV_WZ0 + c, nullptr, zf4, pred4, dst, lane, warp);
-                        else produce8x<true>(c0rows, gvm + GV_WZ0 + c, gvm + GV_WP0 + c, zf4, pred4, dst, lane, warp);
-                        if (kb < 15) load_c0_rows(c0rows, trow4, m * CV_STRIDE + CV_C0 + c + 64);   // lands while the next slot is awaited
-                    } else if (m == 0) produce8<false>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, nullptr, zf4, pred4, dst, lane, warp);
-                    else produce8<true>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, gvm + GV_WP0 + c, zf4, pred4, dst, lane, warp);
-                    ring_publish(e, slot, true);
+                        if (m == 0) produce8x<P, false>(c0rows, gvm + GV_WZ0 + c, nullptr, zf4, pred4, dst, lane, warp, part);
+                        else produce8x<P, true>(c0rows, gvm + GV_WZ0 + c, gvm + GV_WP0 + c, zf4, pred4, dst, lane, warp, part);
+                        if (kb < 15 && part == P - 1) load_c0_rows(c0rows, trow4, m * CV_STRIDE + CV_C0 + c + 64);   // lands while the next slot is awaited
+                    } else if (m == 0) produce8<P, false>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, nullptr, zf4, pred4, dst, lane, warp, part);
+                    else produce8<P, true>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, gvm + GV_WP0 + c, zf4, pred4, dst, lane, warp, part);
+                    ring_publish(e, slot, P == 1);
                 }
-                // E1: layer 1, both halves (bias b1) -> A ring
-                ptx::mbar_wait(&bars->acc_full[0], acc0 & 1u, 20, prof);
-                ptx::tc_fence_after();
-                epilogue_256<false, false>(e, lane_t0, 0, gvm + GV_B1, nullptr, nullptr);
-                ++acc0;
-                ptx::mbar_wait(&bars->acc_full[1], acc1 & 1u, 21, prof);
-                ptx::tc_fence_after();
-                epilogue_256<false, false>(e, lane_t1, 1, gvm + GV_B1 + 256, nullptr, nullptr);
-                ++acc1;
+                if (P != 1) {
+                    // E1 of this half of layer 1 (always T0) -> A ring; layer 2 accumulates into T1 behind it
+                    ptx::mbar_wait(&bars->acc_full[0], acc0 & 1u, 20, prof);
+                    ptx::tc_fence_after();
+                    epilogue_256<P, false, false>(e, lane_t0, 0, gvm + GV_B1 + half * 256, nullptr, nullptr);
+                    ++acc0;
+                }
+                }
+                // P = 1: layer 1 in T0 | T1, layer 2 -> T0, layer 3 -> T1;  P = 3: layer 2 -> T1, layer 3 -> T0
+                const uint32_t lane_l2 = P == 1 ? lane_t0 : lane_t1, lane_l3 = P == 1 ? lane_t1 : lane_t0;
+                uint32_t &acc_l2 = P == 1 ? acc0 : acc1, &acc_l3 = P == 1 ? acc1 : acc0;
+                constexpr int ID_L2 = P == 1 ? 0 : 1, ID_L3 = P == 1 ? 1 : 0;
+                if (P == 1) {
+                    // E1: layer 1, both halves (bias b1) -> A ring
+                    ptx::mbar_wait(&bars->acc_full[0], acc0 & 1u, 20, prof);
+                    ptx::tc_fence_after();
+                    epilogue_256<P, false, false>(e, lane_t0, 0, gvm + GV_B1, nullptr, nullptr);
+                    ++acc0;
+                    ptx::mbar_wait(&bars->acc_full[1], acc1 & 1u, 21, prof);
+                    ptx::tc_fence_after();
+                    epilogue_256<P, false, false>(e, lane_t1, 1, gvm + GV_B1 + 256, nullptr, nullptr);
+                    ++acc1;
+                }
                 // E2: layer 2 + skip terms -> A ring
-                ptx::mbar_wait(&bars->acc_full[0], acc0 & 1u, 22, prof);
+                ptx::mbar_wait(&bars->acc_full[ID_L2], acc_l2 & 1u, 22, prof);
                 ptx::tc_fence_after();
-                if (m == 0) epilogue_256<true, false>(e, lane_t0, 0, cvm + CV_C2, gvm + GV_WZ2, nullptr);
-                else epilogue_256<true, true>(e, lane_t0, 0, cvm + CV_C2, gvm + GV_WZ2, gvm + GV_WP2);
-                ++acc0;
+                if (m == 0) epilogue_256<P, true, false>(e, lane_l2, ID_L2, cvm + CV_C2, gvm + GV_WZ2, nullptr);
+                else epilogue_256<P, true, true>(e, lane_l2, ID_L2, cvm + CV_C2, gvm + GV_WZ2, gvm + GV_WP2);
+                ++acc_l2;
                 // E3: layer 3 + skip terms, layer 4, sigmoid (warps 0-3)
-                ptx::mbar_wait(&bars->acc_full[1], acc1 & 1u, 23, prof);
+                ptx::mbar_wait(&bars->acc_full[ID_L3], acc_l3 & 1u, 23, prof);
                 ptx::tc_fence_after();
                 float logit = 0.0f;
                 if (e.hsel == 0) {
@@ -367,7 +395,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
 #pragma unroll 1
                     for (int q = 0; q < 4; ++q) {
                         uint32_t r[32];
-                        ptx::tmem_ld32(lane_t1 + q * 32, r);
+                        ptx::tmem_ld32(lane_l3 + q * 32, r);
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
@@ -387,8 +415,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { ptx::mbar_arrive(&bars->acc_free[1]); ptx::mbar_arrive(&bars->t1_free_b); }
-                ++acc1;
+                if (lane == 0) {
+                    ptx::mbar_arrive(&bars->acc_free[ID_L3]);
+                    if (P == 1) ptx::mbar_arrive(&bars->t1_free_b);
+                }
+                ++acc_l3;
                 if (e.hsel == 0) {
                     const float pred = pr.mask * (1.0f / (1.0f + expf(-logit)));
                     if (m == 0) {
@@ -444,7 +475,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 for (int c = 0; c < commits; ++c) ptx::umma_commit(&bars->a_free[slot]);
                 ++ablk;
             };
-            for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+            for (int64_t tile = blockIdx.x; P != 1 && tile < prm.ntiles; tile += gridDim.x) {
+                for (int m = 0; m < 2; ++m) {
+                    for (int half = 0; half < 2; ++half) {
+                        // layer 1, one N half: K = 1024 -> T0
+                        ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 33, prof);
+                        ptx::tc_fence_after();
+                        for (int kb = 0; kb < 16 * P; ++kb) {
+                            const uint32_t slot = wait_a();
+                            const uint32_t w = wait_w();
+                            mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
+                            release_w();
+                            release_a(slot, 2);
+                        }
+                        ptx::umma_commit(&bars->acc_full[0]);
+                        ++acc0;
+                        // layer 2, the K half that E1 drains from T0 -> T1
+                        if (half == 0) {
+                            ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 35, prof);
+                            ptx::tc_fence_after();
+                        }
+                        for (int kb = 0; kb < 4 * P; ++kb) {
+                            const uint32_t slot = wait_a();
+                            const uint32_t w = wait_w();
+                            mma_block(T1, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, half == 0 && kb == 0);
+                            release_w();
+                            release_a(slot, 2);
+                        }
+                    }
+                    ptx::umma_commit(&bars->acc_full[1]);
+                    ++acc1;
+                    // layer 3: K = 256, N = 128 -> T0
+                    ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 36, prof);
+                    ptx::tc_fence_after();
+                    for (int kb = 0; kb < 4 * P; ++kb) {
+                        const uint32_t slot = wait_a();
+                        const uint32_t w = wait_w();
+                        mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC128, kb == 0);
+                        release_w();
+                        release_a(slot, 2);
+                    }
+                    ptx::umma_commit(&bars->acc_full[0]);
+                    ++acc0;
+                }
+            }
+            for (int64_t tile = blockIdx.x; P == 1 && tile < prm.ntiles; tile += gridDim.x) {
                 for (int m = 0; m < 2; ++m) {
                     long long tp = PROF ? clock64() : 0;
                     auto phase = [&](int slot) {
@@ -458,7 +533,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 33, prof);
                     ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 34, prof);    // keeps this thread's phase count of acc_free[1]
                     ptx::tc_fence_after();
-                    for (int kb = 0; kb < 16; ++kb) {
+                    for (int kb = 0; kb < 16 * P; ++kb) {
                         const uint32_t slot = wait_a();
                         const uint32_t w = wait_w();
                         if (!(PROF && (prm.ablate & 4))) mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
@@ -472,7 +547,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     // layer 2: K = 512 (y1 halves from E1), N = 256 -> T0
                     ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 35, prof);
                     ptx::tc_fence_after();
-                    for (int kb = 0; kb < 8; ++kb) {
+                    for (int kb = 0; kb < 8 * P; ++kb) {
                         const uint32_t slot = wait_a();
                         const uint32_t w = wait_w();
                         mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
@@ -485,7 +560,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     // layer 3: K = 256, N = 128 -> T1
                     ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 36, prof);
                     ptx::tc_fence_after();
-                    for (int kb = 0; kb < 4; ++kb) {
+                    for (int kb = 0; kb < 4 * P; ++kb) {
                         const uint32_t slot = wait_a();
                         const uint32_t w = wait_w();
                         mma_block(T1, a_smem + slot * A_BLK_BYTES, w, 4, IDESC128, kb == 0);
@@ -500,7 +575,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
         }
     } else if (warp == NEPI + 2) {
         // =============================== MMA issue, T1 half of layer 1 ======================
-        if (lane == 0) {
+        if (lane == 0 && P == 1) {
             constexpr uint32_t IDESC256 = ptx::umma_idesc_f16(128, 256);
             uint32_t wblk = 1, ablk = 0, wph = 0, aph = 0, tph = 0;
             for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
@@ -508,7 +583,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     ptx::mbar_wait(&bars->t1_free_b, tph ^ 1u, 37, nullptr);          // E3 of the previous pass has read T1
                     tph ^= 1u;
                     ptx::tc_fence_after();
-                    for (int kb = 0; kb < 16; ++kb) {
+                    for (int kb = 0; kb < 16 * P; ++kb) {
                         const uint32_t slot = ablk % NA_SLOT, s = wblk % NSTAGE;
                         ptx::mbar_wait(&bars->a_ready_b[slot], (aph >> slot) & 1u, 38, nullptr);
                         aph ^= 1u << slot;
@@ -522,7 +597,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                         ++ablk;
                     }
                     ptx::umma_commit(&bars->acc_full[1]);
-                    wblk += 12; ablk += 12;                       // layers 2 and 3
+                    wblk += 12 * P; ablk += 12 * P;               // layers 2 and 3
                 }
             }
         }
@@ -538,12 +613,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     ptx::tma_load_1d(smem + SMEM_CV + cvb * CV_BYTES, prm.table + (tile / prm.nseg) * CV_ROW_FLOATS, CV_BYTES, &bars->cv_full[cvb]);
                 }
                 const uint8_t *src = prm.weights;
-                for (int b = 0; b < 2 * BLOCKS_PER_MLP; ++b) {
-                    const uint32_t bytes = (b % BLOCKS_PER_MLP) < 40 ? W_BLK_BYTES : W128_BLK_BYTES;
+                for (int b = 0; b < 2 * BLOCKS_PER_MLP * P; ++b) {
+                    const int bm = b % (BLOCKS_PER_MLP * P);
+                    const uint32_t bytes = bm < 40 * P ? W_BLK_BYTES : W128_BLK_BYTES;
                     const uint32_t s = wblk % NSTAGE;
                     ptx::mbar_wait(&bars->empty_w[s], ((wblk / NSTAGE) & 1u) ^ 1u, 40, prof);
                     // odd layer-1 blocks go to the second issuing thread
-                    uint64_t *full = ((b % BLOCKS_PER_MLP) < 32 && (b & 1)) ? &bars->full_wb[s] : &bars->full_w[s];
+                    uint64_t *full = (P == 1 && bm < 32 && (b & 1)) ? &bars->full_wb[s] : &bars->full_w[s];
                     if (PROF && (prm.ablate & 1)) {
                         ptx::mbar_arrive(full);
                     } else {
@@ -567,11 +643,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------
 constexpr int TB_NSTAGE = 3;
 constexpr int TB_THREADS = 6 * 32;
-constexpr int TB_SMEM_F = 0;
-constexpr int TB_SMEM_W = 5 * A_BLK_BYTES;
-constexpr int TB_SMEM_BAR = TB_SMEM_W + TB_NSTAGE * W_BLK_BYTES;
-constexpr int TB_SMEM_TOTAL = TB_SMEM_BAR + 256 + 1024;
 constexpr int TB_CHUNKS = 2 * TB_CHUNKS_PER_MLP;
+// P = 3 (split operands): F as hi + lo tiles (10 K blocks), two weight stages
+template <int P>
+struct TbLayout {
+    static constexpr int NSTAGE = P == 1 ? TB_NSTAGE : 2;
+    static constexpr int SMEM_F = 0;
+    static constexpr int SMEM_W = (P == 1 ? 5 : 10) * A_BLK_BYTES;
+    static constexpr int SMEM_BAR = SMEM_W + NSTAGE * W_BLK_BYTES;
+    static constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;
+    static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
+};
 
 struct TbBars {
     uint64_t full_w[TB_NSTAGE], empty_w[TB_NSTAGE];
@@ -590,8 +672,11 @@ struct TbParams {
     int R1, plane_lo;
 };
 
+template <int P>
 __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_constant__ PointIO io, const __grid_constant__ TbParams prm)
 {
+    using L = TbLayout<P>;
+    constexpr int TB_SMEM_F = L::SMEM_F, TB_SMEM_W = L::SMEM_W, TB_SMEM_BAR = L::SMEM_BAR, NST = L::NSTAGE;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -600,7 +685,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
     TbBars *bars = reinterpret_cast<TbBars *>(smem + TB_SMEM_BAR);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TB_NSTAGE; ++s) { ptx::mbar_init(&bars->full_w[s], 1); ptx::mbar_init(&bars->empty_w[s], 1); }
+        for (int s = 0; s < NST; ++s) { ptx::mbar_init(&bars->full_w[s], 1); ptx::mbar_init(&bars->empty_w[s], 1); }
         for (int t = 0; t < 2; ++t) { ptx::mbar_init(&bars->acc_full[t], 1); ptx::mbar_init(&bars->acc_free[t], 4); }
         ptx::mbar_init(&bars->f_ready, 4);
         ptx::fence_barrier_init();
@@ -621,7 +706,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
             if (!valid) col = prm.ncols - 1;
             const int i = prm.plane_lo + (int)(col / prm.R1), j = (int)(col % prm.R1);
             const Projected pr = project_point(io, (float)io.axis[0][i], (float)io.axis[1][j], (float)io.axis[2][0]);
-            gather_rows<32>(prm.fm, pr, warp * 32, lane, f_smem);
+            if (P == 1) gather_rows<32>(prm.fm, pr, warp * 32, lane, f_smem);
+            else gather_rows_x3<32>(prm.fm, pr, warp * 32, lane, f_smem);
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&bars->f_ready);
@@ -678,12 +764,13 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
                     const int t = ch & 1;
                     ptx::mbar_wait(&bars->acc_free[t], (acc[t] & 1u) ^ 1u, 72);
                     ptx::tc_fence_after();
-                    for (int kb = 0; kb < 5; ++kb) {
-                        const uint32_t s = wblk % TB_NSTAGE;
-                        ptx::mbar_wait(&bars->full_w[s], (wblk / TB_NSTAGE) & 1u, 73);
+                    for (int kp = 0; kp < 5 * P; ++kp) {
+                        const int kb = kp / P, part = kp - kb * P;           // P = 3: F_hi.W_hi, F_lo.W_hi, F_hi.W_lo
+                        const uint32_t s = wblk % NST;
+                        ptx::mbar_wait(&bars->full_w[s], (wblk / NST) & 1u, 73);
                         ptx::tc_fence_after();
-                        mma_block(tmem + t * 256, f_smem + kb * A_BLK_BYTES, w_smem + s * W_BLK_BYTES, 4,
-                                  (ch % TB_CHUNKS_PER_MLP) == 7 ? IDESC144 : IDESC256, kb == 0);
+                        mma_block(tmem + t * 256, f_smem + (kb + (part == 1 ? 5 : 0)) * A_BLK_BYTES, w_smem + s * W_BLK_BYTES, 4,
+                                  (ch % TB_CHUNKS_PER_MLP) == 7 ? IDESC144 : IDESC256, kp == 0);
                         ptx::umma_commit(&bars->empty_w[s]);
                         ++wblk;
                     }
@@ -698,10 +785,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const uint8_t *src = prm.weights;
                 for (int ch = 0; ch < TB_CHUNKS; ++ch)
-                    for (int kb = 0; kb < 5; ++kb) {
+                    for (int kp = 0; kp < 5 * P; ++kp) {
                         const uint32_t bytes = (ch % TB_CHUNKS_PER_MLP) == 7 ? W3_BLK_BYTES : W_BLK_BYTES;
-                        const uint32_t s = wblk % TB_NSTAGE;
-                        ptx::mbar_wait(&bars->empty_w[s], ((wblk / TB_NSTAGE) & 1u) ^ 1u, 74);
+                        const uint32_t s = wblk % NST;
+                        ptx::mbar_wait(&bars->empty_w[s], ((wblk / NST) & 1u) ^ 1u, 74);
                         ptx::mbar_arrive_expect_tx(&bars->full_w[s], bytes);
                         ptx::tma_load_1d(smem + TB_SMEM_W + s * W_BLK_BYTES, src, bytes, &bars->full_w[s]);
                         src += bytes;
@@ -869,6 +956,48 @@ int surs_col_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS
     SURS_CUDA(ctx, cudaMemcpyAsync(dev, host, sizeof(PackDesc) * n, cudaMemcpyHostToDevice, st));
     pack_weights_kernel<<<n, 256, 0, st>>>(dev, base);
     SURS_LAUNCH_CHECK(ctx, "pack_weights_kernel(col)");
+    // split-operand streams (SURS_PREC_FP16X3): every block of the main and table streams three times, as
+    // (W_hi, W_hi, W_lo) -- the A side carries (hi, lo, hi); main stream per MLP: layer 1 rows 0-255, layer 2
+    // K blocks 0-3, layer 1 rows 256-511, layer 2 K blocks 4-7, layer 3
+    {
+        if (!ctx->col_weights_x3) SURS_CUDA(ctx, cudaMalloc(&ctx->col_weights_x3, X3_BYTES));
+        const int n1 = 2 * BLOCKS_PER_MLP + 2 * 40;               // main + table descriptors come first in host[]
+        PackDesc *h3 = new (std::nothrow) PackDesc[3 * n1];
+        if (!h3) SURS_FAIL(ctx, "out of host memory");
+        uint32_t o3 = 0;
+        int n3 = 0;
+        auto emit = [&](int i, int part) {
+            PackDesc d = host[i];
+            d.lo = part == 2;
+            d.out_off = o3;
+            o3 += (uint32_t)d.ntotal * 128u;
+            h3[n3++] = d;
+        };
+        for (int m = 0; m < 2; ++m) {                           // main stream in the order of the P = 3 schedule
+            const int i0 = m * BLOCKS_PER_MLP;
+            for (int half = 0; half < 2; ++half) {
+                for (int kb = 0; kb < 16; ++kb)
+                    for (int part = 0; part < 3; ++part) emit(i0 + 2 * kb + half, part);
+                for (int kb = 0; kb < 4; ++kb)
+                    for (int part = 0; part < 3; ++part) emit(i0 + 32 + 4 * half + kb, part);
+            }
+            for (int kb = 0; kb < 4; ++kb)
+                for (int part = 0; part < 3; ++part) emit(i0 + 40 + kb, part);
+        }
+        for (int i = 2 * BLOCKS_PER_MLP; i < n1; ++i)             // table stream
+            for (int part = 0; part < 3; ++part) emit(i, part);
+        PackDesc *dev3 = nullptr;
+        cudaError_t e3 = o3 == X3_BYTES ? cudaMalloc(&dev3, sizeof(PackDesc) * 3 * n1) : cudaErrorInvalidValue;
+        if (e3 == cudaSuccess) e3 = cudaMemcpyAsync(dev3, h3, sizeof(PackDesc) * 3 * n1, cudaMemcpyHostToDevice, st);
+        if (e3 == cudaSuccess) {
+            pack_weights_kernel<<<3 * n1, 256, 0, st>>>(dev3, (uint8_t *)ctx->col_weights_x3);
+            e3 = cudaStreamSynchronize(st);
+        }
+        delete[] h3;
+        cudaFree(dev3);
+        if (e3 != cudaSuccess) SURS_FAIL(ctx, "packing the split-operand weight streams failed: %s", cudaGetErrorString(e3));
+        ctx->launches++;
+    }
     GvSrc s[2];
     for (int m = 0; m < 2; ++m) {
         for (int l = 0; l < SURS_NUM_LAYERS; ++l) { s[m].w[l] = w[m][l]; s[m].cin[l] = ctx->cin[m][l]; }
@@ -886,38 +1015,44 @@ int surs_col_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS
     return 0;
 }
 
-int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo, int64_t ncols, cudaStream_t st)
+int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo, int64_t ncols, cudaStream_t st, int passes)
 {
     if (surs_ensure(ctx, (void **)&ctx->col_table, &ctx->col_table_cap, (size_t)ncols * CV_ROW_BYTES)) return 1;
     uint8_t *base = (uint8_t *)ctx->col_weights;
     TbParams tb;
-    tb.weights = base + OFF_TABLE;
+    tb.weights = passes == 3 ? (const uint8_t *)ctx->col_weights_x3 + 3 * OFF_TABLE : base + OFF_TABLE;
     for (int m = 0; m < 2; ++m)
         for (int l = 0; l < SURS_NUM_LAYERS; ++l) tb.bias[m][l] = ctx->b32[m][l];
     tb.g0 = reinterpret_cast<const float *>(base + OFF_G0);
     tb.fm.f_lr = ctx->f_lr16; tb.fm.f_hr = ctx->f_hr16;
+    tb.fm.f_lr32 = ctx->f_lr32; tb.fm.f_hr32 = ctx->f_hr32;
     tb.fm.H_lr = ctx->H_lr; tb.fm.W_lr = ctx->W_lr; tb.fm.H_hr = ctx->H_hr; tb.fm.W_hr = ctx->W_hr;
     tb.table = (float *)ctx->col_table;
     tb.ncols = ncols; tb.R1 = R1; tb.plane_lo = plane_lo;
     const int64_t tb_tiles = (ncols + TILE_M - 1) / TILE_M;
     const int tb_grid = (int)(tb_tiles < ctx->sm_count ? tb_tiles : ctx->sm_count);
-    SURS_CUDA(ctx, cudaFuncSetAttribute(col_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_TOTAL));
-    col_table_kernel<<<tb_grid, TB_THREADS, TB_SMEM_TOTAL, st>>>(io, tb);
+    if (passes == 3) {
+        SURS_CUDA(ctx, cudaFuncSetAttribute(col_table_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TbLayout<3>::SMEM_TOTAL));
+        col_table_kernel<3><<<tb_grid, TB_THREADS, TbLayout<3>::SMEM_TOTAL, st>>>(io, tb);
+    } else {
+        SURS_CUDA(ctx, cudaFuncSetAttribute(col_table_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TbLayout<1>::SMEM_TOTAL));
+        col_table_kernel<1><<<tb_grid, TB_THREADS, TbLayout<1>::SMEM_TOTAL, st>>>(io, tb);
+    }
     SURS_LAUNCH_CHECK(ctx, "col_table_kernel");
     return 0;
 }
 
 // Dense slab evaluation through the column-factored kernels.  io: grid mode, lin_base / n / out_* set
 // for planes [plane_lo, plane_lo + nplanes) of a [R0, R1, R2] grid without transform.
-int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st)
+int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st, int passes)
 {
     const int64_t ncols = (int64_t)nplanes * R1;
     if (ncols <= 0) return 0;
-    if (surs_col_build_table(ctx, io, R1, plane_lo, ncols, st)) return 1;
+    if (surs_col_build_table(ctx, io, R1, plane_lo, ncols, st, passes)) return 1;
     uint8_t *base = (uint8_t *)ctx->col_weights;
 
     ColParams prm;
-    prm.weights = base + OFF_MAIN;
+    prm.weights = passes == 3 ? (const uint8_t *)ctx->col_weights_x3 : base + OFF_MAIN;
     prm.gv = reinterpret_cast<const float *>(base + OFF_GV);
     prm.table = (const float *)ctx->col_table;
     prm.nseg = (R2 + TILE_M - 1) / TILE_M;
@@ -926,16 +1061,22 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
     prm.ablate = getenv("SURS_COL_ABLATE") ? atoi(getenv("SURS_COL_ABLATE")) : 0;
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
     static const bool profile = getenv("SURS_TC_PROFILE") != nullptr;
+    if (passes == 3) {
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        query_col_kernel<false, false, 3><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+        SURS_LAUNCH_CHECK(ctx, "query_col_kernel<x3>");
+        return 0;
+    }
     if (!profile) {
-        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        query_col_kernel<false, false><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        query_col_kernel<false, false, 1><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
         SURS_LAUNCH_CHECK(ctx, "query_col_kernel");
         return 0;
     }
     unsigned long long zero[64] = {0}, h[64];
     SURS_CUDA(ctx, cudaMemcpyToSymbol(g_col_prof, zero, sizeof(zero)));
-    SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    query_col_kernel<true, false><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+    SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    query_col_kernel<true, false, 1><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
     SURS_LAUNCH_CHECK(ctx, "query_col_kernel<profile>");
     SURS_CUDA(ctx, cudaStreamSynchronize(st));
     SURS_CUDA(ctx, cudaMemcpyFromSymbol(h, g_col_prof, sizeof(h)));
@@ -951,12 +1092,12 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
 // Octree levels through the column table: io is in grid mode with idx_list / vol_* set (n selected nodes of a
 // [R0, R1, R2] grid without transform); the table must cover all R0 x R1 columns (surs_col_build_table with
 // plane_lo = 0), built once per reconstruction.
-int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int R2, cudaStream_t st)
+int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int R2, cudaStream_t st, int passes)
 {
     if (io.n <= 0) return 0;
     uint8_t *base = (uint8_t *)ctx->col_weights;
     ColParams prm;
-    prm.weights = base + OFF_MAIN;
+    prm.weights = passes == 3 ? (const uint8_t *)ctx->col_weights_x3 : base + OFF_MAIN;
     prm.gv = reinterpret_cast<const float *>(base + OFF_GV);
     prm.table = (const float *)ctx->col_table;
     prm.nseg = 1;
@@ -964,8 +1105,13 @@ int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int 
     prm.R1 = R1; prm.R2 = R2; prm.plane_lo = 0;
     prm.ablate = 0;
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
-    SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    query_col_kernel<false, true><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+    if (passes == 3) {
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        query_col_kernel<false, true, 3><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+    } else {
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        query_col_kernel<false, true, 1><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+    }
     SURS_LAUNCH_CHECK(ctx, "query_col_kernel<indexed>");
     return 0;
 }

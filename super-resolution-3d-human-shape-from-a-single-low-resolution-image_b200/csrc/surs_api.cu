@@ -66,6 +66,7 @@ extern "C" void surs_destroy(surs_ctx *ctx)
     cudaFree(ctx->tc_weights);
     cudaFree(ctx->tc_scratch);
     cudaFree(ctx->col_weights);
+    cudaFree(ctx->col_weights_x3);
     cudaFree(ctx->col_table);
     cudaFree(ctx->f_lr32); cudaFree(ctx->f_hr32); cudaFree(ctx->f_lr16); cudaFree(ctx->f_hr16);
     cudaFree(ctx->axis_dev); cudaFree(ctx->dirty); cudaFree(ctx->idx_list); cudaFree(ctx->counter);
@@ -193,13 +194,15 @@ static int check_ready(surs_ctx *ctx, int precision)
 {
     if (!ctx->have_weights) SURS_FAIL(ctx, "surs_set_weights has not been called");
     if (!ctx->have_features) SURS_FAIL(ctx, "surs_set_features has not been called");
-    if (precision != SURS_PREC_FP32 && precision != SURS_PREC_FP16) SURS_FAIL(ctx, "unknown precision %d", precision);
+    if (precision != SURS_PREC_FP32 && precision != SURS_PREC_FP16 && precision != SURS_PREC_FP16X3) SURS_FAIL(ctx, "unknown precision %d", precision);
     return 0;
 }
 
 static int run_query(surs_ctx *ctx, const PointIO &io, int precision, cudaStream_t st)
 {
-    return precision == SURS_PREC_FP32 ? surs_launch_query_simt(ctx, io, st) : surs_launch_query_tc(ctx, io, st);
+    // SURS_PREC_FP16X3 has tensor-core kernels for column-factored grids only (query_col.cu); every other point
+    // source runs the exact CUDA-core kernel, which is the more accurate of the two
+    return precision == SURS_PREC_FP16 ? surs_launch_query_tc(ctx, io, st) : surs_launch_query_simt(ctx, io, st);
 }
 
 static void fill_proj(PointIO &io, const float calib[12], float z_num, float z_den)
@@ -304,9 +307,11 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
     // SURS_COL_INC=1: layer 1 by incremental updates along the column (query_inc.cu; exact but, as measured,
     // slower than the GEMM of query_col.cu -- experiments/README.md).  Read per call so that tests can toggle it.
     const bool col_inc = getenv("SURS_COL_INC") != nullptr;
-    if (precision == SURS_PREC_FP16 && !transform && calib[2] == 0.0f && calib[6] == 0.0f && res[2] >= 64 && !no_column)
+    if (precision != SURS_PREC_FP32 && !transform && calib[2] == 0.0f && calib[6] == 0.0f && res[2] >= 64 && !no_column) {
+        if (precision == SURS_PREC_FP16X3) return surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st, 3);
         return col_inc ? surs_launch_query_inc(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st)
                        : surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st);
+    }
     // one launch handles < 2^31 CTAs; split very large slabs
     const int64_t chunk = (int64_t)1 << 30;
     for (int64_t s = 0; s < io.n; s += chunk) {
@@ -369,8 +374,9 @@ extern "C" int surs_eval_grid_octree(surs_ctx *ctx, const int res[3], const doub
     io.vol_lr = sdf_lr;
     // Column-table path (same preconditions as the dense column kernels): every W.f product once per column,
     // for all levels; the levels then run the indexed variant of query_col_kernel.  SURS_NO_COLUMN=1 disables it.
-    const bool use_table = precision == SURS_PREC_FP16 && !transform && calib[2] == 0.0f && calib[6] == 0.0f && getenv("SURS_NO_COLUMN") == nullptr;
-    if (use_table && surs_col_build_table(ctx, io, res[1], 0, (int64_t)res[0] * res[1], st)) return 1;
+    const int passes = precision == SURS_PREC_FP16X3 ? 3 : 1;
+    const bool use_table = precision != SURS_PREC_FP32 && !transform && calib[2] == 0.0f && calib[6] == 0.0f && getenv("SURS_NO_COLUMN") == nullptr;
+    if (use_table && surs_col_build_table(ctx, io, res[1], 0, (int64_t)res[0] * res[1], st, passes)) return 1;
     while (reso > 0) {
         const size_t cand = (size_t)((res[0] + reso - 1) / reso) * ((res[1] + reso - 1) / reso) * ((res[2] + reso - 1) / reso);
         if (surs_ensure(ctx, (void **)&ctx->idx_list, &ctx->idx_cap, cand * sizeof(int64_t))) return 1;
@@ -382,7 +388,7 @@ extern "C" int surs_eval_grid_octree(surs_ctx *ctx, const int res[3], const doub
             PointIO part = io;
             part.idx_list = ctx->idx_list + s;
             part.n = (nsel - s < chunk) ? nsel - s : chunk;
-            if (use_table ? surs_launch_query_col_indexed(ctx, part, res[1], res[2], st) : run_query(ctx, part, precision, st)) return 1;
+            if (use_table ? surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, passes) : run_query(ctx, part, precision, st)) return 1;
         }
         if (reso <= 1) break;                                   // lib/sdf.py:79
         if (surs_octree_cells_impl(ctx, res, reso, threshold, sdf_hr, sdf_lr, ctx->dirty, st)) return 1;

@@ -37,6 +37,24 @@ __device__ __forceinline__ uint32_t leaky_h2(float a, float b)
     return *reinterpret_cast<const uint32_t *>(&r);
 }
 
+// Split-operand ("x3") mode: leaky_relu in fp32, then the value as fp16 hi (part 0 / 2) or as the fp16
+// residual lo = fp16(y - hi) (part 1).  A.W is evaluated as A_hi.W_hi + A_lo.W_hi + A_hi.W_lo on the tensor
+// cores (fp32 accumulate): the dropped A_lo.W_lo term and the rounding of the residuals are ~2^-22 relative.
+__device__ __forceinline__ uint32_t split_h2(float a, float b, int part)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    if (part != 1) return *reinterpret_cast<const uint32_t *>(&h);
+    const float2 f = __half22float2(h);
+    return pack_h2(a - f.x, b - f.y);
+}
+// P = 1: packed half2 leaky_relu; P = 3: fp32 leaky_relu + hi / lo split
+template <int P>
+__device__ __forceinline__ uint32_t act_h2(float a, float b, int part)
+{
+    if (P == 1) return leaky_h2(a, b);
+    return split_h2(leaky(a), leaky(b), part);
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v)
 {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -55,6 +73,7 @@ __device__ __forceinline__ void accum_tap(float (&acc)[8], uint4 v, float w)
 
 struct FeatMaps {
     const __half *f_lr, *f_hr;                 // channels-last fp16
+    const float *f_lr32, *f_hr32;              // channels-last fp32 (split-operand mode)
     int H_lr, W_lr, H_hr, W_hr;
 };
 
@@ -101,6 +120,51 @@ __device__ __forceinline__ void gather_rows(const FeatMaps &fm, const Projected 
     }
 }
 
+// Split-operand variant: bilinear gather in fp32 from the fp32 maps (exactly lib/geometry.py:4-12), written
+// as an fp16 hi tile (5 K blocks at f_smem) and an fp16 lo = fp16(f - hi) tile (5 K blocks behind it).
+template <int NROWS>
+__device__ __forceinline__ void gather_rows_x3(const FeatMaps &fm, const Projected &pr, int row0, int lane, uint32_t f_smem)
+{
+    const Taps tl = make_taps(pr.u, pr.v, fm.H_lr, fm.W_lr);
+    const Taps th = make_taps(pr.u, pr.v, fm.H_hr, fm.W_hr);
+    auto tap = [](float (&acc)[8], const float *src, float w) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), b = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+        acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+        acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+    };
+    auto store = [&](const float (&acc)[8], uint32_t dst) {
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            const uint4 o = make_uint4(split_h2(acc[0], acc[1], part), split_h2(acc[2], acc[3], part),
+                                       split_h2(acc[4], acc[5], part), split_h2(acc[6], acc[7], part));
+            st_shared_v4(dst + part * 5 * A_BLK_BYTES, o);
+        }
+    };
+#pragma unroll 4
+    for (int p = 0; p < NROWS; ++p) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int off = __shfl_sync(0xffffffffu, tl.off[q], p);
+            const float w = __shfl_sync(0xffffffffu, tl.w[q], p);
+            if (off >= 0) tap(acc, fm.f_lr32 + (size_t)off * SURS_C_LR + lane * 8, w);
+        }
+        store(acc, f_smem + (lane >> 3) * A_BLK_BYTES + sw128_off(row0 + p, lane & 7));
+    }
+#pragma unroll
+    for (int it = 0; it < NROWS / 4; ++it) {
+        const int p = it * 4 + (lane >> 3);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int off = __shfl_sync(0xffffffffu, th.off[q], p);
+            const float w = __shfl_sync(0xffffffffu, th.w[q], p);
+            if (off >= 0) tap(acc, fm.f_hr32 + (size_t)off * SURS_C_HR + (lane & 7) * 8, w);
+        }
+        store(acc, f_smem + 4 * A_BLK_BYTES + sw128_off(row0 + p, lane & 7));
+    }
+}
+
 // K-major MMAs over one 64-wide (or 16-wide tail) K block: D[tmem_d] (+)= A[a_addr] . B[w_addr]^T
 __device__ __forceinline__ void mma_block(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int ksteps, uint32_t idesc, bool zero_first)
 {
@@ -125,6 +189,7 @@ struct PackDesc {
     int bias_only;         // tail block that carries nothing but the bias (layer 1)
     int k0, k0_extra;      // first column (plain) / start of the skip part (F-order)
     int c0;                // 321 / 322: width of the skip input
+    int lo;                // split-operand streams: pack the residual w - fp16(w) instead of w
     uint32_t out_off;
 };
 
@@ -168,7 +233,7 @@ static __global__ void pack_weights_kernel(const PackDesc *descs, uint8_t *out)
                         x = col == -2 ? hi : b - hi;
                     }
                 }
-                v[j] = x;
+                v[j] = d.lo ? x - __half2float(__float2half_rn(x)) : x;
             }
             packed[i] = pack_h2(v[0], v[1]);
         }
