@@ -166,7 +166,7 @@ def run_ours(args):
     zn, zd = float(case.load_size // 2), float(case.z_size)
     b_min, b_max = np.array([-0.5] * 3), np.array([0.5] * 3)
     mat = bsdf.grid_matrix(res, b_min, b_max)
-    prec = _capi.PREC_FP32 if args.precision == "fp32" else _capi.PREC_FP16
+    prec = {"fp32": _capi.PREC_FP32, "fp16": _capi.PREC_FP16, "fp16x3": _capi.PREC_FP16X3}[args.precision]
     n_queries = res ** 3
 
     def step():
@@ -217,9 +217,11 @@ def run_ours(args):
     # dense grids with an axis-aligned calibration take the column-factored kernels (query_col.cu): the
     # products of the weights with the 320 image channels are computed once per (i,j) column, so the
     # EXECUTED tensor-core work is 2 x 1 376 256 MAC per point (layers 1-3 only) + the per-column table
-    executed_flop = 2 * 2 * (512 * 1024 + 256 * 512 + 128 * 256) if prec == _capi.PREC_FP16 else FLOP_PER_QUERY
+    col_flop = 2 * 2 * (512 * 1024 + 256 * 512 + 128 * 256)
+    # fp16x3: every product as A_hi.W_hi + A_lo.W_hi + A_hi.W_lo = three times the tensor-core work
+    executed_flop = {_capi.PREC_FP16: col_flop, _capi.PREC_FP16X3: 3 * col_flop}.get(prec, FLOP_PER_QUERY)
     executed = n_slab * executed_flop / (q_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "query_col_kernel (+ col_table_kernel)" if prec == _capi.PREC_FP16 else "query_simt_kernel",
+    roofline = {"bound": "tensor", "kernel": "query_col_kernel (+ col_table_kernel)" if prec != _capi.PREC_FP32 else "query_simt_kernel",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one query_col_kernel launch at 512^3, ncu --set full
                 # (profiles/r1_ncu_full_r13_col512.csv): 3.03 GB per-column table read + 1.07 GB volumes written
@@ -279,7 +281,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f16" if prec == _capi.PREC_FP16 else "f32", "data": "synthetic",
+            "dtype": {"fp16": "f16", "fp16x3": "f16x3", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": "dense %d^3 reconstruction (query + marching cubes of HR and LR volumes%s), one synthetic %dx%d input, "
                                    "random-init MLP weights" % (res, ", slab-sharded + NCCL mesh gather" if world > 1 else "", args.size, args.size),
                        "resolution": res, "input_side": args.size, "precision": args.precision,
@@ -305,7 +307,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--resolution", type=int, default=512)
     ap.add_argument("--size", type=int, default=512, help="side of the synthetic low-res input image")
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp16x3", "fp32"],
+                    help="fp16: one tensor-core pass (headline); fp16x3: split hi/lo operands, three passes (|d occ| ~2e-5); fp32: CUDA cores")
     ap.add_argument("--cpu-points", type=int, default=400000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
