@@ -233,6 +233,32 @@ def run_ours(args):
                         "column factoring removes 40% of the MACs (exact refactoring, not skipped work). executed_* counts the MACs the "
                         "tensor cores really ran (fp16 operands, fp32 accumulate = the bf16 rate)"}
 
+    # ---- the split-operand mode beside the headline (N = 1): same step, SURS_PREC_FP16X3 -----------------
+    accurate = None
+    if world == 1 and prec == _capi.PREC_FP16 and not args.no_x3:
+        def step3():
+            return parallel.reconstruct_slab(ctx, (res, res, res), b_min, b_max, case.calib, zn, zd, mat[:3, :4], precision=_capi.PREC_FP16X3)
+        step3()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(2):
+            step3()
+        b.record()
+        torch.cuda.synchronize(dev)
+        ms3 = a.elapsed_time(b) / 2
+        # parity of both tensor modes against the fp32 CUDA-core mode on one plane of the grid (res^2 nodes)
+        mid = res // 2
+        v32 = ctx.eval_grid((res, res, res), b_min, b_max, case.calib, zn, zd, precision=_capi.PREC_FP32, plane_lo=mid, plane_hi=mid + 1)
+        v16 = ctx.eval_grid((res, res, res), b_min, b_max, case.calib, zn, zd, precision=_capi.PREC_FP16, plane_lo=mid, plane_hi=mid + 1)
+        vx3 = ctx.eval_grid((res, res, res), b_min, b_max, case.calib, zn, zd, precision=_capi.PREC_FP16X3, plane_lo=mid, plane_hi=mid + 1)
+        dmax = lambda u, v: max(float((u[0] - v[0]).abs().max()), float((u[1] - v[1]).abs().max()))
+        accurate = {"precision": "fp16x3", "value": n_queries / (ms3 * 1e-3), "unit": "queries/s", "ms_per_step": ms3,
+                    "executed_tflops": n_queries * 3 * col_flop / (ms3 * 1e-3) / 1e12,
+                    "max_abs_diff_vs_fp32_mode": {"fp16x3": dmax(vx3, v32), "fp16": dmax(v16, v32), "nodes": res * res,
+                                                  "note": "pre-threshold occupancy, plane %d of the grid; north_star example tolerance 1e-3" % mid}}
+        del v32, v16, vx3
+
     # ---- end to end through the public API with host buffers ------------------------------------
     e2e = None
     if rank == 0 and world == 1 and not args.no_e2e:
@@ -275,7 +301,20 @@ def run_ours(args):
         rate, dt, threads = cpu_query_rate(case, args.cpu_points)
         cpu = {"value": rate, "unit": "queries/s", "cores": threads, "kind": "port",
                "sample": "%d random nodes of the 512^3 grid in 50 000-point chunks through the torch CPU port of the reference "
-                         "query (%.1f s); marching cubes not included" % (args.cpu_points, dt)}
+                         "query (%.1f s); marching cubes timed separately (mc_*)" % (args.cpu_points, dt)}
+        # the other half of the reference's CPU path (skimage marching cubes, lib/mesh_util.py:40,45): the oracle's
+        # scalar C twin on the 128^3 volumes of BASELINE config 1, one host thread like skimage's Cython loop
+        from oracle import mc_oracle
+        v128 = ctx.eval_grid((128, 128, 128), b_min, b_max, case.calib, zn, zd, precision=prec)
+        mc_s = 0.0
+        for v in v128:
+            vh = v.cpu().numpy()
+            t0 = time.perf_counter()
+            mc_oracle.marching_cubes_lewiner(vh, 0.5)
+            mc_s += time.perf_counter() - t0
+        cpu["mc_port_s_both_volumes_128cubed"] = mc_s
+        cpu["s_per_mesh_128cubed_estimate"] = 128 ** 3 / rate + mc_s
+        cpu["s_per_mesh_512cubed_estimate"] = 512 ** 3 / rate + mc_s * 16      # surface cells scale with R^2
 
     if rank == 0:
         line = {
@@ -293,6 +332,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "accurate_mode": accurate,
         }
         print(json.dumps(line))
     if world > 1:
@@ -311,6 +351,7 @@ def main():
                     help="fp16: one tensor-core pass (headline); fp16x3: split hi/lo operands, three passes (|d occ| ~2e-5); fp32: CUDA cores")
     ap.add_argument("--cpu-points", type=int, default=400000)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-x3", action="store_true", help="skip the fp16x3 (split-operand) measurement beside the headline")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -83,9 +83,10 @@ def test_query_api_matches_reference_semantics(case32, golden_dir):
     assert np.abs(net.preds_hr[0, 0].detach().cpu().numpy() - g["pred_hr"]).max() < 1e-4
 
 
-@pytest.mark.parametrize("use_octree,res", [(False, 64), (True, 128)])
-def test_reconstruction_fast_path(case32, use_octree, res):
-    opt, net = make_net(case32)
+@pytest.mark.parametrize("use_octree,res,prec", [(False, 64, _capi.PREC_FP16), (True, 128, _capi.PREC_FP16),
+                                                 (False, 64, _capi.PREC_FP16X3), (True, 128, _capi.PREC_FP16X3)])
+def test_reconstruction_fast_path(case32, use_octree, res, prec):
+    opt, net = make_net(case32, precision=prec)
     calib = torch.from_numpy(case32.calib)[None].to(DEV)
     b_min, b_max = np.array([-0.5] * 3), np.array([0.5] * 3)
     out, stats = mesh_util.reconstruction(opt, net, DEV, calib, res, b_min, b_max, use_octree=use_octree, return_stats=True)
@@ -93,11 +94,11 @@ def test_reconstruction_fast_path(case32, use_octree, res):
     ctx = net.surs_context()
     zn, zd = net.depth_scale()
     if use_octree:
-        a, b, n_eval = ctx.eval_grid_octree((res,) * 3, b_min, b_max, calib, zn, zd, opt.threshold)
+        a, b, n_eval = ctx.eval_grid_octree((res,) * 3, b_min, b_max, calib, zn, zd, opt.threshold, precision=prec)
         vols = (a.float(), b.float())
         assert stats["n_evaluated"] == n_eval < res ** 3
     else:
-        vols = ctx.eval_grid((res,) * 3, b_min, b_max, calib, zn, zd)
+        vols = ctx.eval_grid((res,) * 3, b_min, b_max, calib, zn, zd, precision=prec)
     _, mat = O.create_grid(res, res, res, b_min, b_max)
     for k, vol in enumerate(vols):
         v, f, n, val = mc_oracle.marching_cubes_lewiner(vol.cpu().numpy(), 0.5)
