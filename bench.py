@@ -180,7 +180,10 @@ def run_ours(args):
     for _ in range(args.warmup):
         out = step()
     barrier()
-    launches0 = ctx.launches
+    def n_launches():                                    # the LR mesh goes through a sibling context at N > 1 (parallel.py)
+        sib = getattr(ctx, "_mc_sibling", None)
+        return ctx.launches + (sib.launches if sib is not None else 0)
+    launches0 = n_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         e0.record()
@@ -189,7 +192,7 @@ def run_ours(args):
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
-    launches = ctx.launches - launches0
+    launches = n_launches() - launches0
     tt = torch.tensor([ms_total], device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -8,11 +8,15 @@ exchanges are
   2. the seam: ids of the vertices lying in the plane shared by two slabs travel from the lower
      rank to the upper one (2 x res^2 int32 per mesh), so that the concatenated mesh is
      bit-identical to the single-GPU one (same vertex numbering, no duplicates), and
-  3. the gather of the vertex / face lists to rank 0.
+  3. the gather of the vertex / face lists to rank 0
+(each of the three once per step for BOTH meshes: the point-to-point operations are batched into one NCCL group).
 Rank r evaluates planes [lo_r, hi_r + 1) (the halo plane is recomputed, not exchanged) and
 meshes the cells whose lower plane it owns; axis 0 is the outermost scan axis of the marching
 cubes, so concatenation in rank order *is* the single-volume order.
 """
+import os
+import time
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -77,11 +81,64 @@ def pass_up(tensor_out, tensor_in, group=None):
             w.wait()
 
 
+def gather_rows_many(items, dst=0, group=None):
+    """``gather_rows`` for several tensors in ONE batch of point-to-point operations (one NCCL group launch
+    instead of one per tensor).  items: [(local, counts_per_rank), ...]; returns the list of concatenations on
+    ``dst`` (None elsewhere; ``local`` itself when there is one rank)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return [local for local, _ in items]
+    ops, outs, keep = [], [], []
+    for local, counts in items:
+        counts = [int(c) for c in counts]
+        if rank == dst:
+            out = torch.empty((sum(counts),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+            offs = np.cumsum([0] + counts)
+            out[offs[dst]:offs[dst + 1]] = local
+            ops += [dist.P2POp(dist.irecv, out[offs[r]:offs[r + 1]], r, group) for r in range(world) if r != dst and counts[r] > 0]
+            outs.append(out)
+        else:
+            if counts[rank] > 0:
+                keep.append(local.contiguous())
+                ops.append(dist.P2POp(dist.isend, keep[-1], dst, group))
+            outs.append(None)
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return outs
+
+
+def pass_up_many(pairs, group=None):
+    """``pass_up`` for several (tensor_out, tensor_in) pairs in one batch."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ops = []
+    for tensor_out, tensor_in in pairs:
+        if rank + 1 < world:
+            ops.append(dist.P2POp(dist.isend, tensor_out, rank + 1, group))
+        if rank > 0:
+            ops.append(dist.P2POp(dist.irecv, tensor_in, rank - 1, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def _mc_contexts(ctx):
+    """Marching-cubes state lives in the context between count and emit; a sibling context on the same device
+    lets the HR and the LR volume go through count -> exchange -> emit together (one exchange round for both)."""
+    sib = getattr(ctx, "_mc_sibling", None)
+    if sib is None:
+        sib = _capi.Context(ctx.device)
+        ctx._mc_sibling = sib
+    return ctx, sib
+
+
 def reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, transform=None, precision=_capi.PREC_FP16,
                      group=None, gather=True, want_normals=True):
     """Dense reconstruction of this rank's slab + the mesh exchange.  Returns on rank 0 the same
     8-tuple pieces as lib.mesh_util.reconstruction but as device tensors:
-    ((world_hr, faces_hr, normals_hr, values_hr), (world_lr, ...)); other ranks get (None, None)."""
+    ((world_hr, faces_hr, normals_hr, values_hr), (world_lr, ...)); other ranks get (None, None).
+    Exchange rounds per step (both meshes together): one all-gather of 4 counts, one seam hand-over,
+    one batched gather of the vertex / face lists."""
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     rank = dist.get_rank(group) if distributed else 0
     world = dist.get_world_size(group) if distributed else 1
@@ -92,29 +149,61 @@ def reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, transform
                          plane_lo=lo, plane_hi=hi_halo)
     flags = _capi.MC_LOWER_FOREIGN if rank > 0 else 0
     dev = ctx.device
-    results = []
-    for vol in vols:                                   # HR first, then LR (lib/mesh_util.py:40,45)
-        nv, nf, _ = ctx.mc_count(vol, MC_LEVEL, flags)
-        if distributed:
-            mine = torch.tensor([nv, nf], device=dev, dtype=torch.int64)
-            allc = torch.empty((world, 2), device=dev, dtype=torch.int64)
-            dist.all_gather_into_tensor(allc, mine, group=group)
-            allc = allc.cpu().numpy()
-        else:
-            allc = np.array([[nv, nf]], dtype=np.int64)
-        v_off = int(exclusive_offsets(allc)[rank, 0])
-        seam_out = torch.empty((2, R1, R2), device=dev, dtype=torch.int32) if distributed and rank + 1 < world else None
-        verts, world_v, normals, values = ctx.mc_emit_verts(nv, mat, vert_id_offset=v_off, seam_out=seam_out,
-                                                            want_normals=want_normals, plane_offset=lo)
+    ctxs = _mc_contexts(ctx) if distributed else (ctx, ctx)
+    timing = os.environ.get("SURS_TIMING") is not None and rank == 0
+    t_last = [0.0]
+
+    def tick(label):
+        if timing:
+            torch.cuda.synchronize(dev)
+            now = time.perf_counter()
+            if label:
+                print("[surs timing rank0] %-28s %8.3f ms" % (label, (now - t_last[0]) * 1e3), flush=True)
+            t_last[0] = now
+    tick("grid evaluation" if timing and t_last[0] else None)
+    if not distributed:
+        results = []
+        for vol in vols:                               # HR first, then LR (lib/mesh_util.py:40,45)
+            nv, nf, _ = ctx.mc_count(vol, MC_LEVEL, flags)
+            _, world_v, normals, values = ctx.mc_emit_verts(nv, mat, want_normals=want_normals, plane_offset=lo)
+            results.append((world_v, ctx.mc_emit_faces(nf), normals, values))
+        return tuple(results)
+    counts = [c.mc_count(vol, MC_LEVEL, flags)[:2] for c, vol in zip(ctxs, vols)]
+    tick("mc_count x2")
+    mine = torch.tensor([counts[0][0], counts[0][1], counts[1][0], counts[1][1]], device=dev, dtype=torch.int64)
+    allc = torch.empty((world, 4), device=dev, dtype=torch.int64)
+    dist.all_gather_into_tensor(allc, mine, group=group)
+    allc = allc.cpu().numpy()
+    offs = exclusive_offsets(allc)
+    tick("all-gather of the counts")
+    emitted, seams = [], []
+    for k, c in enumerate(ctxs):
+        seam_out = torch.empty((2, R1, R2), device=dev, dtype=torch.int32) if rank + 1 < world else None
         seam_in = torch.empty((2, R1, R2), device=dev, dtype=torch.int32) if rank > 0 else None
-        if distributed:
-            pass_up(seam_out, seam_in, group)
-        faces = ctx.mc_emit_faces(nf, seam_in=seam_in)
-        if distributed and gather:
-            world_v = gather_rows(world_v, allc[:, 0], 0, group)
-            faces = gather_rows(faces, allc[:, 1], 0, group)
-            if want_normals:
-                normals = gather_rows(normals, allc[:, 0], 0, group)
-                values = gather_rows(values, allc[:, 0], 0, group)
-        results.append((world_v, faces, normals, values) if rank == 0 or not gather else None)
+        _, world_v, normals, values = c.mc_emit_verts(counts[k][0], mat, vert_id_offset=int(offs[rank, 2 * k]), seam_out=seam_out,
+                                                      want_normals=want_normals, plane_offset=lo)
+        emitted.append([world_v, None, normals, values])
+        seams.append((seam_out, seam_in))
+    tick("emit vertices x2")
+    pass_up_many(seams, group)
+    tick("seam hand-over")
+    for k, c in enumerate(ctxs):
+        emitted[k][1] = c.mc_emit_faces(counts[k][1], seam_in=seams[k][1])
+    tick("emit faces x2")
+    if not gather:
+        return tuple(tuple(e) for e in emitted)
+    items = []
+    for k, e in enumerate(emitted):
+        items += [(e[0], allc[:, 2 * k]), (e[1], allc[:, 2 * k + 1])]
+        if want_normals:
+            items += [(e[2], allc[:, 2 * k]), (e[3], allc[:, 2 * k])]
+    got = gather_rows_many(items, 0, group)
+    tick("gather of the mesh lists")
+    if rank != 0:
+        return (None, None)
+    per = 4 if want_normals else 2
+    results = []
+    for k in range(2):
+        g = got[per * k:per * (k + 1)]
+        results.append((g[0], g[1], g[2], g[3]) if want_normals else (g[0], g[1], None, None))
     return tuple(results)

@@ -52,11 +52,20 @@ def _worker(rank, world, port, out):
         seam_out = torch.full((2, 4, 4), rank, dtype=torch.int32)
         seam_in = torch.full((2, 4, 4), -7, dtype=torch.int32)
         parallel.pass_up(seam_out, seam_in)
+        # the batched variants (one group of point-to-point operations for several tensors)
+        counts2 = counts[::-1]
+        local2 = torch.arange(counts2[rank], dtype=torch.int32) - 50 * rank
+        many = parallel.gather_rows_many([(local, counts), (local2, counts2)], 0)
+        seams = [(torch.full((2, 3), 10 * k + rank, dtype=torch.int32), torch.full((2, 3), -7, dtype=torch.int32)) for k in range(2)]
+        parallel.pass_up_many(seams)
         if rank == 0:
             want = torch.cat([torch.arange(c * 3, dtype=torch.float32).reshape(c, 3) + 100 * r for r, c in enumerate(counts)])
+            want2 = torch.cat([torch.arange(c, dtype=torch.int32) - 50 * r for r, c in enumerate(counts2)])
             ok = torch.equal(got, want) and bool((seam_in == -7).all())
+            ok = ok and torch.equal(many[0], want) and torch.equal(many[1], want2) and all(bool((si == -7).all()) for _, si in seams)
         else:
             ok = got is None and bool((seam_in == rank - 1).all())
+            ok = ok and many == [None, None] and all(bool((si == 10 * k + rank - 1).all()) for k, (_, si) in enumerate(seams))
         out.put((rank, ok))
     finally:
         dist.destroy_process_group()
