@@ -16,7 +16,7 @@ def launches(path):
     tot = sum(a[1] for a in agg.values())
     print("kernel,launches,total_ms,share_pct")
     for n, a in sorted(agg.items(), key=lambda x: -x[1][1]):
-        print("%s,%d,%.3f,%.2f" % (n, a[0], a[1], 100 * a[1] / tot))
+        csv.writer(sys.stdout).writerow([n, a[0], "%.3f" % a[1], "%.2f" % (100 * a[1] / tot)])
 
 WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
@@ -31,10 +31,11 @@ def raw(path):
     rows = list(csv.reader(out.splitlines()))
     names, units = rows[0], rows[1]
     kn = names.index('Kernel Name')
-    idx = [(i, n) for i, n in enumerate(names) if n in WANT]
-    print("kernel," + ",".join("%s [%s]" % (n, units[i]) for i, n in idx))
+    idx = [(i, n) for i, n in enumerate(names) if n in WANT or any(n.endswith('.' + w) for w in WANT)]
+    w = csv.writer(sys.stdout)
+    w.writerow(["kernel"] + ["%s [%s]" % (n, units[i]) for i, n in idx])
     for r in rows[2:]:
-        print(r[kn].split('(')[0].replace('<unnamed>::', '') + "," + ",".join(r[i] for i, _ in idx))
+        w.writerow([r[kn].split('(')[0].replace('<unnamed>::', '')] + [r[i] for i, _ in idx])
 
 if __name__ == '__main__':
     if sys.argv[1] == 'launches': launches(sys.argv[2])
