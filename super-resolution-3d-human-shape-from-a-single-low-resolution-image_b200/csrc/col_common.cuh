@@ -52,7 +52,9 @@ constexpr size_t OFF_XW = OFF_RSTAR + 2 * 512 * 4;
 constexpr size_t OFF_XV = OFF_XW + 2 * XW_MLP_BYTES;
 constexpr size_t OFF_W1H = (OFF_XV + XV_BYTES + 255) / 256 * 256;    // fp16 W1^T [2][1024][512] (query_inc.cu events)
 constexpr size_t COL_WEIGHTS_BYTES = OFF_W1H + (size_t)2 * 1024 * 512 * 2;
-constexpr size_t X3_BYTES = 3 * OFF_GV;                  // split-operand copy of the main + table streams (surs_ctx::col_weights_x3)
+// split-operand copy of the streams (surs_ctx::col_weights_x3): main stream as (hi, lo) pairs, table stream as (hi, hi, lo)
+constexpr size_t X3_TABLE_OFF = 2 * OFF_TABLE;
+constexpr size_t X3_BYTES = X3_TABLE_OFF + 3 * (OFF_GV - OFF_TABLE);
 static_assert(OFF_XW % 1024 == 0 && OFF_TABLE % 1024 == 0, "operand blocks must stay 1024-byte aligned");
 
 }  // namespace col

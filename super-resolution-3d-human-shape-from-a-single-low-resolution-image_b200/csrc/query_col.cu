@@ -31,23 +31,29 @@ namespace {
 
 using namespace col;
 
-constexpr int NSTAGE = 4;
-constexpr int NA_SLOT = 3;
+// ring depths: P = 1 (one pass) 4 weight stages + 3 A slots; P = 3 (split operands) 3 + 4: a K block is a
+// (hi, lo) slot pair there, so four slots hold two K blocks
+template <int P> struct Ring {
+    static constexpr int NSTAGE = P == 1 ? 4 : 3;
+    static constexpr int NA_SLOT = P == 1 ? 3 : 4;
+    static constexpr int AP = P == 1 ? 1 : 2;            // A blocks per K block (hi | hi, lo)
+    static constexpr int WP = P == 1 ? 1 : 2;            // weight blocks per K block (hi | hi, lo)
+    static constexpr int SMEM_W = 0;
+    static constexpr int SMEM_A = SMEM_W + NSTAGE * W_BLK_BYTES;
+    static constexpr int SMEM_CV = SMEM_A + NA_SLOT * A_BLK_BYTES;
+    static constexpr int SMEM_GV = SMEM_CV + 2 * CV_BYTES;
+    static constexpr int SMEM_BAR = SMEM_GV + GV_BYTES;
+    static constexpr int SMEM_PREDX = SMEM_BAR + 256;   // pred_lr hand-over between the two warps of a quarter
+    static constexpr int SMEM_TOTAL = SMEM_PREDX + 512 + 1024;
+    static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
+};
 constexpr int BLOCKS_PER_MLP = 32 + 8 + 4;
 constexpr int KBLK_PER_MLP = 16 + 4 + 4 + 4;             // A-ring K blocks per MLP
 constexpr int NEPI = 8;
 constexpr int NTHREADS = (NEPI + 3) * 32;            // + MMA issue, weight stream, second MMA issue
 
-constexpr int SMEM_W = 0;
-constexpr int SMEM_A = SMEM_W + NSTAGE * W_BLK_BYTES;
-constexpr int SMEM_CV = SMEM_A + NA_SLOT * A_BLK_BYTES;
-constexpr int SMEM_GV = SMEM_CV + 2 * CV_BYTES;
-constexpr int SMEM_BAR = SMEM_GV + GV_BYTES;
-constexpr int SMEM_PREDX = SMEM_BAR + 256;               // pred_lr hand-over between the two warps of a quarter
-constexpr int SMEM_TOTAL = SMEM_PREDX + 512 + 1024;
-static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
-
-struct Bars {
+template <int NSTAGE, int NA_SLOT>
+struct BarsT {
     uint64_t full_w[NSTAGE], empty_w[NSTAGE];
     uint64_t a_ready[NA_SLOT], a_free[NA_SLOT];
     uint64_t acc_full[2], acc_free[2];
@@ -57,7 +63,7 @@ struct Bars {
     uint64_t full_wb[NSTAGE], a_ready_b[NA_SLOT], t1_free_b;
     uint32_t tmem_base;
 };
-static_assert(sizeof(Bars) <= 256, "barrier block");
+static_assert(sizeof(BarsT<4, 3>) <= 256 && sizeof(BarsT<3, 4>) <= 256, "barrier block");
 
 struct ColParams {
     const uint8_t *weights;        // 2 x MLP_BYTES
@@ -176,7 +182,8 @@ __device__ __forceinline__ void produce8x(const C0Rows &c0, const float *wz, con
 }
 
 struct EpiCtx {
-    Bars *bars;
+    uint64_t *a_ready, *a_ready_b, *a_free, *acc_free;   // barrier arrays of the kernel's BarsT
+    uint32_t nslot;
     uint32_t a_smem;
     int row, hsel, lane;
     float zf, pred;
@@ -186,8 +193,8 @@ struct EpiCtx {
 
 __device__ __forceinline__ uint32_t ring_acquire(EpiCtx &e)
 {
-    const uint32_t slot = e.g % NA_SLOT;
-    ptx::mbar_wait(&e.bars->a_free[slot], ((e.g / NA_SLOT) & 1u) ^ 1u, 10, e.prof);
+    const uint32_t slot = e.g % e.nslot;
+    ptx::mbar_wait(&e.a_free[slot], ((e.g / e.nslot) & 1u) ^ 1u, 10, e.prof);
     return slot;
 }
 __device__ __forceinline__ void ring_publish(EpiCtx &e, uint32_t slot, bool layer0 = false)   // layer0: the block feeds the second issuing thread too
@@ -195,8 +202,8 @@ __device__ __forceinline__ void ring_publish(EpiCtx &e, uint32_t slot, bool laye
     ptx::fence_proxy_async_smem();
     __syncwarp();
     if (e.lane == 0) {
-        ptx::mbar_arrive(&e.bars->a_ready[slot]);
-        if (layer0) ptx::mbar_arrive(&e.bars->a_ready_b[slot]);    // layer-0 blocks feed both halves of layer 1
+        ptx::mbar_arrive(&e.a_ready[slot]);
+        if (layer0) ptx::mbar_arrive(&e.a_ready_b[slot]);          // layer-0 blocks feed both halves of layer 1
     }
     ++e.g;
 }
@@ -216,11 +223,11 @@ __device__ __forceinline__ void epilogue_256(EpiCtx &e, uint32_t taddr, int acc_
         } else {
             ptx::tc_fence_before();
             __syncwarp();
-            if (e.lane == 0) ptx::mbar_arrive(&e.bars->acc_free[acc_id]);
+            if (e.lane == 0) ptx::mbar_arrive(&e.acc_free[acc_id]);
         }
         const int c = kb * 64 + e.hsel * 32;
 #pragma unroll 1
-        for (int part = 0; part < P; ++part) {                 // P = 3: the K block goes out as hi, lo, hi
+        for (int part = 0; part < Ring<P>::AP; ++part) {       // P = 3: the K block goes out as a (hi, lo) slot pair
             const uint32_t slot = ring_acquire(e);
             finish32<P, true, HAS_Z, HAS_P>(r[kb & 1], add + c, wz + c, wp + c, e.zf, e.pred, e.a_smem + slot * A_BLK_BYTES, e.row, e.hsel, part);
             ring_publish(e, slot);
@@ -234,10 +241,10 @@ __device__ unsigned long long g_col_prof[64];
 // one column; column vectors are read per row from the table of ALL columns (plane_lo = 0), results are
 // scattered with pointio_store.
 // P = 3 (SURS_PREC_FP16X3): every K block of layers 1-3 is issued three times -- A_hi.W_hi, A_lo.W_hi, A_hi.W_lo --
-// from an A ring that carries (hi, lo, hi) and a weight stream that carries (hi, hi, lo).  The schedule differs
-// from P = 1: an accumulator may only be released after its last column has been read, and with three ring
-// slots per K block E1 could no longer park three K blocks in the ring while layer 2 waits for the accumulator
-// it is reading.  So layer 1 runs as two sequential N halves into T0 (layer 0 is produced twice), layer 2
+// from an A ring that carries the block as a (hi, lo) slot pair and a weight stream that carries it as (hi, lo).
+// The schedule differs from P = 1: an accumulator may only be released after its last column has been read, and
+// with two ring slots per K block E1 can no longer park three K blocks in the ring while layer 2 waits for the
+// accumulator it is reading.  So layer 1 runs as two sequential N halves into T0 (layer 0 is produced twice), layer 2
 // accumulates into T1 behind each half, layer 3 goes to T0 -- the accumulator being drained is never the one the
 // consumer of the drained blocks writes to.  One issuing thread; warp NEPI + 2 idles.
 template <bool PROF, bool INDEXED, int P>
@@ -247,11 +254,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
     const uint32_t raw = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - raw);
+    using RG = Ring<P>;
+    constexpr int NSTAGE = RG::NSTAGE, NA_SLOT = RG::NA_SLOT, AP = RG::AP;
+    constexpr int SMEM_W = RG::SMEM_W, SMEM_A = RG::SMEM_A, SMEM_CV = RG::SMEM_CV, SMEM_GV = RG::SMEM_GV;
+    using Bars = BarsT<NSTAGE, NA_SLOT>;
     const uint32_t a_smem = base + SMEM_A, w_smem = base + SMEM_W;
     float *cv_s = reinterpret_cast<float *>(smem + SMEM_CV);
     float *gv_s = reinterpret_cast<float *>(smem + SMEM_GV);
-    Bars *bars = reinterpret_cast<Bars *>(smem + SMEM_BAR);
-    float *pred_x = reinterpret_cast<float *>(smem + SMEM_PREDX);
+    Bars *bars = reinterpret_cast<Bars *>(smem + RG::SMEM_BAR);
+    float *pred_x = reinterpret_cast<float *>(smem + RG::SMEM_PREDX);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long *prof = nullptr;
     if (PROF && lane == 0 && (warp == 0 || warp == NEPI || warp == NEPI + 1)) prof = g_col_prof;
@@ -260,7 +271,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&bars->full_w[s], 1); ptx::mbar_init(&bars->empty_w[s], 1); }
         for (int k = 0; k < NA_SLOT; ++k) {
-            ptx::mbar_init(&bars->a_ready[k], NEPI); ptx::mbar_init(&bars->a_ready_b[k], NEPI); ptx::mbar_init(&bars->a_free[k], 2);
+            ptx::mbar_init(&bars->a_ready[k], NEPI); ptx::mbar_init(&bars->a_ready_b[k], NEPI);
+            ptx::mbar_init(&bars->a_free[k], P == 1 ? 2 : 1);          // P = 1: one commit from each issuing thread
         }
         for (int s = 0; s < NSTAGE; ++s) ptx::mbar_init(&bars->full_wb[s], 1);
         ptx::mbar_init(&bars->t1_free_b, NEPI);
@@ -282,7 +294,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
     if (warp < NEPI) {
         // =============================== y0 production + epilogues ========================
         EpiCtx e;
-        e.bars = bars; e.a_smem = a_smem; e.lane = lane; e.prof = prof; e.g = 0;
+        e.a_ready = bars->a_ready; e.a_ready_b = bars->a_ready_b; e.a_free = bars->a_free; e.acc_free = bars->acc_free;
+        e.nslot = NA_SLOT; e.a_smem = a_smem; e.lane = lane; e.prof = prof; e.g = 0;
         const int quarter = warp & 3;
         e.hsel = warp >> 2;
         e.row = quarter * 32 + lane;
@@ -342,8 +355,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 for (int half = 0; half < (P == 1 ? 1 : 2); ++half) {
                 if (INDEXED) load_c0_rows(c0rows, trow4, m * CV_STRIDE + CV_C0 + warp * 8);
 #pragma unroll 1
-                for (int kp = 0; kp < 16 * P; ++kp) {
-                    const int kb = kp / P, part = kp - kb * P;
+                for (int kp = 0; kp < 16 * AP; ++kp) {
+                    const int kb = kp / AP, part = kp - kb * AP;
                     const uint32_t slot = ring_acquire(e);
                     const int c = kb * 64 + warp * 8;                    // warp w fills 16-byte chunk w of all 128 rows
                     const uint32_t dst = a_smem + slot * A_BLK_BYTES;
@@ -352,7 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     } else if (INDEXED) {
                         if (m == 0) produce8x<P, false>(c0rows, gvm + GV_WZ0 + c, nullptr, zf4, pred4, dst, lane, warp, part);
                         else produce8x<P, true>(c0rows, gvm + GV_WZ0 + c, gvm + GV_WP0 + c, zf4, pred4, dst, lane, warp, part);
-                        if (kb < 15 && part == P - 1) load_c0_rows(c0rows, trow4, m * CV_STRIDE + CV_C0 + c + 64);   // lands while the next slot is awaited
+                        if (kb < 15 && part == AP - 1) load_c0_rows(c0rows, trow4, m * CV_STRIDE + CV_C0 + c + 64);   // lands while the next slot is awaited
                     } else if (m == 0) produce8<P, false>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, nullptr, zf4, pred4, dst, lane, warp, part);
                     else produce8<P, true>(cvm + CV_C0 + c, gvm + GV_WZ0 + c, gvm + GV_WP0 + c, zf4, pred4, dst, lane, warp, part);
                     ring_publish(e, slot, P == 1);
@@ -475,19 +488,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 for (int c = 0; c < commits; ++c) ptx::umma_commit(&bars->a_free[slot]);
                 ++ablk;
             };
+            // P = 3: one K block = A slots (hi, lo) x weight blocks (hi, lo): A_hi.W_hi, A_lo.W_hi, A_hi.W_lo --
+            // twelve MMAs behind four waits and four commits
+            auto kblock3 = [&](uint32_t tmem_d, uint32_t idesc, bool zero_first) {
+                const uint32_t s_hi = wait_a();
+                const uint32_t w_hi = wait_w();
+                mma_block(tmem_d, a_smem + s_hi * A_BLK_BYTES, w_hi, 4, idesc, zero_first);
+                ++ablk;
+                const uint32_t s_lo = wait_a();
+                mma_block(tmem_d, a_smem + s_lo * A_BLK_BYTES, w_hi, 4, idesc, false);
+                release_w();
+                const uint32_t w_lo = wait_w();
+                mma_block(tmem_d, a_smem + s_hi * A_BLK_BYTES, w_lo, 4, idesc, false);
+                release_w();
+                ptx::umma_commit(&bars->a_free[s_hi]);
+                ptx::umma_commit(&bars->a_free[s_lo]);
+                ++ablk;
+            };
             for (int64_t tile = blockIdx.x; P != 1 && tile < prm.ntiles; tile += gridDim.x) {
                 for (int m = 0; m < 2; ++m) {
                     for (int half = 0; half < 2; ++half) {
                         // layer 1, one N half: K = 1024 -> T0
                         ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 33, prof);
                         ptx::tc_fence_after();
-                        for (int kb = 0; kb < 16 * P; ++kb) {
-                            const uint32_t slot = wait_a();
-                            const uint32_t w = wait_w();
-                            mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
-                            release_w();
-                            release_a(slot, 2);
-                        }
+                        for (int kb = 0; kb < 16; ++kb) kblock3(T0, IDESC256, kb == 0);
                         ptx::umma_commit(&bars->acc_full[0]);
                         ++acc0;
                         // layer 2, the K half that E1 drains from T0 -> T1
@@ -495,26 +519,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                             ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 35, prof);
                             ptx::tc_fence_after();
                         }
-                        for (int kb = 0; kb < 4 * P; ++kb) {
-                            const uint32_t slot = wait_a();
-                            const uint32_t w = wait_w();
-                            mma_block(T1, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, half == 0 && kb == 0);
-                            release_w();
-                            release_a(slot, 2);
-                        }
+                        for (int kb = 0; kb < 4; ++kb) kblock3(T1, IDESC256, half == 0 && kb == 0);
                     }
                     ptx::umma_commit(&bars->acc_full[1]);
                     ++acc1;
                     // layer 3: K = 256, N = 128 -> T0
                     ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 36, prof);
                     ptx::tc_fence_after();
-                    for (int kb = 0; kb < 4 * P; ++kb) {
-                        const uint32_t slot = wait_a();
-                        const uint32_t w = wait_w();
-                        mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC128, kb == 0);
-                        release_w();
-                        release_a(slot, 2);
-                    }
+                    for (int kb = 0; kb < 4; ++kb) kblock3(T0, IDESC128, kb == 0);
                     ptx::umma_commit(&bars->acc_full[0]);
                     ++acc0;
                 }
@@ -533,7 +545,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 33, prof);
                     ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 34, prof);    // keeps this thread's phase count of acc_free[1]
                     ptx::tc_fence_after();
-                    for (int kb = 0; kb < 16 * P; ++kb) {
+                    for (int kb = 0; kb < 16; ++kb) {
                         const uint32_t slot = wait_a();
                         const uint32_t w = wait_w();
                         if (!(PROF && (prm.ablate & 4))) mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
@@ -547,7 +559,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     // layer 2: K = 512 (y1 halves from E1), N = 256 -> T0
                     ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 35, prof);
                     ptx::tc_fence_after();
-                    for (int kb = 0; kb < 8 * P; ++kb) {
+                    for (int kb = 0; kb < 8; ++kb) {
                         const uint32_t slot = wait_a();
                         const uint32_t w = wait_w();
                         mma_block(T0, a_smem + slot * A_BLK_BYTES, w, 4, IDESC256, kb == 0);
@@ -560,7 +572,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     // layer 3: K = 256, N = 128 -> T1
                     ptx::mbar_wait(&bars->acc_free[1], (acc1 & 1u) ^ 1u, 36, prof);
                     ptx::tc_fence_after();
-                    for (int kb = 0; kb < 4 * P; ++kb) {
+                    for (int kb = 0; kb < 4; ++kb) {
                         const uint32_t slot = wait_a();
                         const uint32_t w = wait_w();
                         mma_block(T1, a_smem + slot * A_BLK_BYTES, w, 4, IDESC128, kb == 0);
@@ -583,7 +595,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     ptx::mbar_wait(&bars->t1_free_b, tph ^ 1u, 37, nullptr);          // E3 of the previous pass has read T1
                     tph ^= 1u;
                     ptx::tc_fence_after();
-                    for (int kb = 0; kb < 16 * P; ++kb) {
+                    for (int kb = 0; kb < 16; ++kb) {
                         const uint32_t slot = ablk % NA_SLOT, s = wblk % NSTAGE;
                         ptx::mbar_wait(&bars->a_ready_b[slot], (aph >> slot) & 1u, 38, nullptr);
                         aph ^= 1u << slot;
@@ -597,7 +609,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                         ++ablk;
                     }
                     ptx::umma_commit(&bars->acc_full[1]);
-                    wblk += 12 * P; ablk += 12 * P;               // layers 2 and 3
+                    wblk += 12; ablk += 12;                       // layers 2 and 3
                 }
             }
         }
@@ -613,9 +625,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     ptx::tma_load_1d(smem + SMEM_CV + cvb * CV_BYTES, prm.table + (tile / prm.nseg) * CV_ROW_FLOATS, CV_BYTES, &bars->cv_full[cvb]);
                 }
                 const uint8_t *src = prm.weights;
-                for (int b = 0; b < 2 * BLOCKS_PER_MLP * P; ++b) {
-                    const int bm = b % (BLOCKS_PER_MLP * P);
-                    const uint32_t bytes = bm < 40 * P ? W_BLK_BYTES : W128_BLK_BYTES;
+                for (int b = 0; b < 2 * BLOCKS_PER_MLP * RG::WP; ++b) {
+                    const int bm = b % (BLOCKS_PER_MLP * RG::WP);
+                    const uint32_t bytes = bm < 40 * RG::WP ? W_BLK_BYTES : W128_BLK_BYTES;
                     const uint32_t s = wblk % NSTAGE;
                     ptx::mbar_wait(&bars->empty_w[s], ((wblk / NSTAGE) & 1u) ^ 1u, 40, prof);
                     // odd layer-1 blocks go to the second issuing thread
@@ -956,9 +968,10 @@ int surs_col_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS
     SURS_CUDA(ctx, cudaMemcpyAsync(dev, host, sizeof(PackDesc) * n, cudaMemcpyHostToDevice, st));
     pack_weights_kernel<<<n, 256, 0, st>>>(dev, base);
     SURS_LAUNCH_CHECK(ctx, "pack_weights_kernel(col)");
-    // split-operand streams (SURS_PREC_FP16X3): every block of the main and table streams three times, as
-    // (W_hi, W_hi, W_lo) -- the A side carries (hi, lo, hi); main stream per MLP: layer 1 rows 0-255, layer 2
-    // K blocks 0-3, layer 1 rows 256-511, layer 2 K blocks 4-7, layer 3
+    // split-operand streams (SURS_PREC_FP16X3).  Main stream: every block as (W_hi, W_lo) -- the A side is a (hi, lo)
+    // slot pair and the kernel issues A_hi.W_hi, A_lo.W_hi, A_hi.W_lo; per MLP: layer 1 rows 0-255, layer 2
+    // K blocks 0-3, layer 1 rows 256-511, layer 2 K blocks 4-7, layer 3.  Table stream: every block three times as
+    // (W_hi, W_hi, W_lo) against F blocks (hi, lo, hi)
     {
         if (!ctx->col_weights_x3) SURS_CUDA(ctx, cudaMalloc(&ctx->col_weights_x3, X3_BYTES));
         const int n1 = 2 * BLOCKS_PER_MLP + 2 * 40;               // main + table descriptors come first in host[]
@@ -977,20 +990,21 @@ int surs_col_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS
             const int i0 = m * BLOCKS_PER_MLP;
             for (int half = 0; half < 2; ++half) {
                 for (int kb = 0; kb < 16; ++kb)
-                    for (int part = 0; part < 3; ++part) emit(i0 + 2 * kb + half, part);
+                    for (int part = 1; part < 3; ++part) emit(i0 + 2 * kb + half, part);
                 for (int kb = 0; kb < 4; ++kb)
-                    for (int part = 0; part < 3; ++part) emit(i0 + 32 + 4 * half + kb, part);
+                    for (int part = 1; part < 3; ++part) emit(i0 + 32 + 4 * half + kb, part);
             }
             for (int kb = 0; kb < 4; ++kb)
-                for (int part = 0; part < 3; ++part) emit(i0 + 40 + kb, part);
+                for (int part = 1; part < 3; ++part) emit(i0 + 40 + kb, part);
         }
+        if (o3 != X3_TABLE_OFF) { delete[] h3; SURS_FAIL(ctx, "internal: split-operand main stream size mismatch"); }
         for (int i = 2 * BLOCKS_PER_MLP; i < n1; ++i)             // table stream
             for (int part = 0; part < 3; ++part) emit(i, part);
         PackDesc *dev3 = nullptr;
-        cudaError_t e3 = o3 == X3_BYTES ? cudaMalloc(&dev3, sizeof(PackDesc) * 3 * n1) : cudaErrorInvalidValue;
-        if (e3 == cudaSuccess) e3 = cudaMemcpyAsync(dev3, h3, sizeof(PackDesc) * 3 * n1, cudaMemcpyHostToDevice, st);
+        cudaError_t e3 = o3 == X3_BYTES ? cudaMalloc(&dev3, sizeof(PackDesc) * n3) : cudaErrorInvalidValue;
+        if (e3 == cudaSuccess) e3 = cudaMemcpyAsync(dev3, h3, sizeof(PackDesc) * n3, cudaMemcpyHostToDevice, st);
         if (e3 == cudaSuccess) {
-            pack_weights_kernel<<<3 * n1, 256, 0, st>>>(dev3, (uint8_t *)ctx->col_weights_x3);
+            pack_weights_kernel<<<n3, 256, 0, st>>>(dev3, (uint8_t *)ctx->col_weights_x3);
             e3 = cudaStreamSynchronize(st);
         }
         delete[] h3;
@@ -1020,7 +1034,7 @@ int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo,
     if (surs_ensure(ctx, (void **)&ctx->col_table, &ctx->col_table_cap, (size_t)ncols * CV_ROW_BYTES)) return 1;
     uint8_t *base = (uint8_t *)ctx->col_weights;
     TbParams tb;
-    tb.weights = passes == 3 ? (const uint8_t *)ctx->col_weights_x3 + 3 * OFF_TABLE : base + OFF_TABLE;
+    tb.weights = passes == 3 ? (const uint8_t *)ctx->col_weights_x3 + X3_TABLE_OFF : base + OFF_TABLE;
     for (int m = 0; m < 2; ++m)
         for (int l = 0; l < SURS_NUM_LAYERS; ++l) tb.bias[m][l] = ctx->b32[m][l];
     tb.g0 = reinterpret_cast<const float *>(base + OFF_G0);
@@ -1062,21 +1076,21 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
     static const bool profile = getenv("SURS_TC_PROFILE") != nullptr;
     if (passes == 3) {
-        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        query_col_kernel<false, false, 3><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<3>::SMEM_TOTAL));
+        query_col_kernel<false, false, 3><<<grid, NTHREADS, Ring<3>::SMEM_TOTAL, st>>>(io, prm);
         SURS_LAUNCH_CHECK(ctx, "query_col_kernel<x3>");
         return 0;
     }
     if (!profile) {
-        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        query_col_kernel<false, false, 1><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<1>::SMEM_TOTAL));
+        query_col_kernel<false, false, 1><<<grid, NTHREADS, Ring<1>::SMEM_TOTAL, st>>>(io, prm);
         SURS_LAUNCH_CHECK(ctx, "query_col_kernel");
         return 0;
     }
     unsigned long long zero[64] = {0}, h[64];
     SURS_CUDA(ctx, cudaMemcpyToSymbol(g_col_prof, zero, sizeof(zero)));
-    SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    query_col_kernel<true, false, 1><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+    SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<1>::SMEM_TOTAL));
+    query_col_kernel<true, false, 1><<<grid, NTHREADS, Ring<1>::SMEM_TOTAL, st>>>(io, prm);
     SURS_LAUNCH_CHECK(ctx, "query_col_kernel<profile>");
     SURS_CUDA(ctx, cudaStreamSynchronize(st));
     SURS_CUDA(ctx, cudaMemcpyFromSymbol(h, g_col_prof, sizeof(h)));
@@ -1106,11 +1120,11 @@ int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int 
     prm.ablate = 0;
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
     if (passes == 3) {
-        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        query_col_kernel<false, true, 3><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<3>::SMEM_TOTAL));
+        query_col_kernel<false, true, 3><<<grid, NTHREADS, Ring<3>::SMEM_TOTAL, st>>>(io, prm);
     } else {
-        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        query_col_kernel<false, true, 1><<<grid, NTHREADS, SMEM_TOTAL, st>>>(io, prm);
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<1>::SMEM_TOTAL));
+        query_col_kernel<false, true, 1><<<grid, NTHREADS, Ring<1>::SMEM_TOTAL, st>>>(io, prm);
     }
     SURS_LAUNCH_CHECK(ctx, "query_col_kernel<indexed>");
     return 0;

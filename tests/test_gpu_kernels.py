@@ -149,6 +149,25 @@ def test_dense_grid_matches_reference_volumes(ctx, case32, golden_dir):
     assert torch.equal(a[0], b[0].reshape(-1)) and torch.equal(a[1], b[1].reshape(-1))
 
 
+def test_column_kernels_match_reference_reconstruction_volumes(ctx, case32, golden_dir):
+    """The 64^3 volumes captured from the UNMODIFIED reference's lib.mesh_util.reconstruction (real SuRSNet, CPU fp32;
+    tests/golden/make_golden.py) against the column-factored kernels, one-pass and split-operand, dense and through
+    the octree entry point (which at R = 64 = init_resolution evaluates every node, lib/sdf.py:66-79)."""
+    from surs_b200 import _capi
+    g = np.load(os.path.join(golden_dir, "recon_golden.npz"))
+    args = ((64, 64, 64), [-0.5] * 3, [0.5] * 3, case32.calib) + znum(case32)
+    for prec, tol in ((_capi.PREC_FP16, TOL_FP16_MAX), (_capi.PREC_FP16X3, TOL_X3_MAX), (_capi.PREC_FP32, TOL_FP32)):
+        hr, lr = ctx.eval_grid(*args, precision=prec)
+        ohr, olr, n_eval = ctx.eval_grid_octree(*args, threshold=0.05, init_resolution=64, precision=prec)
+        assert n_eval == 64 ** 3
+        for got, want in ((hr, g["oct64_hr"]), (lr, g["oct64_lr"]), (ohr.float(), g["oct64_hr"]), (olr.float(), g["oct64_lr"])):
+            d = np.abs(got.cpu().numpy() - want)
+            print("precision %d vs reference reconstruction volume: max|d| %.3g mean %.3g" % (prec, d.max(), d.mean()))
+            assert d.max() < tol
+        if prec != _capi.PREC_FP32:                       # dense and indexed column kernels: node for node identical
+            assert torch.equal(hr, ohr.float()) and torch.equal(lr, olr.float())
+
+
 def test_octree_blocks_match_reference_golden(ctx, golden_dir):
     """select / cells kernels driven by the analytic eval_func: bit exact vs lib/sdf.py's output."""
     g = np.load(os.path.join(golden_dir, "octree_golden.npz"))
