@@ -3,8 +3,13 @@
 #include "common.cuh"
 #include "col_common.cuh"
 
+#include <algorithm>
+#include <chrono>
+#include <cmath>
 #include <new>
 #include <stdlib.h>
+#include <thread>
+#include <vector>
 
 static char g_create_err[512] = "";
 
@@ -419,24 +424,109 @@ extern "C" int surs_cast_f64_f32(surs_ctx *ctx, const double *src, float *dst, i
 // ------------------------------------------------------------------------------------
 // OBJ writer (host): lib/mesh_util.py:53-61
 // ------------------------------------------------------------------------------------
+// The text is formatted by all host threads (chunks of 64 K lines, written in order): a 512^3 octree mesh is
+// 12 M vertices + 23 M faces, and one thread's snprintf would dominate the whole gen_mesh call.
+namespace {
+struct ObjChunk {
+    std::vector<char> buf;
+    size_t used = 0;
+    char *room(size_t n)
+    {
+        if (buf.size() - used < n) buf.resize(buf.size() * 2 + n);
+        return buf.data() + used;
+    }
+};
+// "%.4f" without printf for the common case.  printf rounds the EXACT binary value half-to-even at the fourth
+// decimal; s = |x| * 1e4 carries a relative rounding error of 2^-53, so for |x| < 1e5 (error < 6e-8 in s) the
+// rounding direction is certain unless frac(s) lies within 1e-6 of 0.5 -- those (and non-finite / large values)
+// go through snprintf, which keeps the file byte-identical to the reference's '%.4f' (lib/mesh_util.py:56).
+inline size_t put_uint(char *dst, uint64_t v)
+{
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    for (int i = 0; i < n; ++i) dst[i] = tmp[n - 1 - i];
+    return (size_t)n;
+}
+inline size_t put_fixed4(char *dst, double x)
+{
+    const double ax = fabs(x);
+    if (!(ax < 1e5)) return (size_t)snprintf(dst, 400, "%.4f", x);
+    const double sc = ax * 10000.0, fl = floor(sc), frac = sc - fl;
+    if (fabs(frac - 0.5) < 1e-6) return (size_t)snprintf(dst, 400, "%.4f", x);
+    const uint64_t n = (uint64_t)fl + (frac > 0.5 ? 1u : 0u);
+    size_t k = 0;
+    if (std::signbit(x)) dst[k++] = '-';
+    k += put_uint(dst + k, n / 10000);
+    const unsigned q = (unsigned)(n % 10000);
+    dst[k++] = '.';
+    dst[k++] = (char)('0' + q / 1000); dst[k++] = (char)('0' + q / 100 % 10);
+    dst[k++] = (char)('0' + q / 10 % 10); dst[k++] = (char)('0' + q % 10);
+    return k;
+}
+inline size_t put_int(char *dst, int64_t v)
+{
+    if (v < 0) { dst[0] = '-'; return 1 + put_uint(dst + 1, (uint64_t)(-v)); }
+    return put_uint(dst, (uint64_t)v);
+}
+
+void obj_format_chunk(ObjChunk &c, const double *verts, int64_t n_verts, const int32_t *faces, int64_t lo, int64_t hi)
+{
+    c.used = 0;
+    if (c.buf.empty()) c.buf.resize((size_t)(hi - lo) * 40 + 1024);
+    for (int64_t i = lo; i < hi; ++i) {
+        char *dst = c.room(1400);
+        size_t k = 0;
+        if (i < n_verts) {
+            dst[k++] = 'v';
+            for (int a = 0; a < 3; ++a) { dst[k++] = ' '; k += put_fixed4(dst + k, verts[3 * i + a]); }
+        } else {
+            const int64_t t = i - n_verts;                          // lib/mesh_util.py:58-60: 1-based, winding flipped
+            dst[k++] = 'f';
+            dst[k++] = ' '; k += put_int(dst + k, (int64_t)faces[3 * t] + 1);
+            dst[k++] = ' '; k += put_int(dst + k, (int64_t)faces[3 * t + 2] + 1);
+            dst[k++] = ' '; k += put_int(dst + k, (int64_t)faces[3 * t + 1] + 1);
+        }
+        dst[k++] = '\n';
+        c.used += k;
+    }
+}
+}  // namespace
+
 extern "C" int surs_save_obj_mesh(const char *path, const double *verts, int64_t n_verts,
                                   const int32_t *faces, int64_t n_faces)
 {
     FILE *f = fopen(path, "w");
     if (!f) return 1;
-    static const size_t BUF = 1 << 20;
-    char *buf = (char *)malloc(BUF + 256);
-    if (!buf) { fclose(f); return 1; }
-    size_t used = 0;
-    for (int64_t i = 0; i < n_verts; ++i) {
-        used += (size_t)snprintf(buf + used, 256, "v %.4f %.4f %.4f\n", verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]);
-        if (used >= BUF) { fwrite(buf, 1, used, f); used = 0; }
+    const int64_t total = n_verts + n_faces, chunk = 1 << 16;
+    const int64_t nchunks = (total + chunk - 1) / chunk;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(hw ? hw : 1, 32), nchunks));
+    bool ok = true;
+    const bool timing = getenv("SURS_TIMING") != nullptr;
+    double t_fmt = 0.0, t_io = 0.0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    try {
+        std::vector<ObjChunk> chunks(nthreads);
+        for (int64_t c0 = 0; c0 < nchunks && ok; c0 += nthreads) {
+            const int n = (int)std::min<int64_t>(nthreads, nchunks - c0);
+            auto work = [&](int t) {
+                const int64_t lo = (c0 + t) * chunk, hi = std::min(total, lo + chunk);
+                obj_format_chunk(chunks[t], verts, n_verts, faces, lo, hi);
+            };
+            const double t0 = now();
+            std::vector<std::thread> pool;
+            for (int t = 1; t < n; ++t) pool.emplace_back(work, t);
+            work(0);
+            for (auto &th : pool) th.join();
+            const double t1 = now();
+            for (int t = 0; t < n && ok; ++t) ok = fwrite(chunks[t].buf.data(), 1, chunks[t].used, f) == chunks[t].used;
+            t_fmt += t1 - t0;
+            t_io += now() - t1;
+        }
+    } catch (...) {
+        ok = false;
     }
-    for (int64_t i = 0; i < n_faces; ++i) {
-        used += (size_t)snprintf(buf + used, 256, "f %d %d %d\n", faces[3 * i] + 1, faces[3 * i + 2] + 1, faces[3 * i + 1] + 1);
-        if (used >= BUF) { fwrite(buf, 1, used, f); used = 0; }
-    }
-    if (used) fwrite(buf, 1, used, f);
-    free(buf);
-    return fclose(f) != 0;
+    if (timing) fprintf(stderr, "[surs timing] obj writer: %d threads, format %.1f ms, fwrite %.1f ms\n", nthreads, t_fmt * 1e3, t_io * 1e3);
+    return (fclose(f) != 0 || !ok) ? 1 : 0;
 }
