@@ -76,10 +76,12 @@ def main():
         torch.cuda.synchronize(dev)
         return t1 - t0, time.perf_counter() - t1, out, stats
 
-    one()
+    for _ in range(3):          # warm-up while the previous result is still referenced, as a caller would hold it:
+        held = one()            # two generations of pinned staging buffers end up in torch's host cache
+    del held
     barrier()
     t0 = time.perf_counter()
-    reps = 2
+    reps = 3
     enc = rec = 0.0
     for _ in range(reps):
         e, r, out, stats = one()
@@ -100,6 +102,10 @@ def main():
     torch.cuda.empty_cache()
 
     # ---------------- C5 ----------------
+    if os.environ.get("SURS_SKIP_C5"):
+        if world > 1:
+            dist.destroy_process_group()
+        return
     case = syn.SyntheticCase(S=512, seed=0)
     ctx = _capi.Context(dev)
     t = lambda a: torch.from_numpy(a).to(dev)

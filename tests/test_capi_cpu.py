@@ -55,6 +55,18 @@ def test_obj_writer_matches_reference(capi, tmp_path, golden_dir):
     f = rng.integers(0, 5000, (9000, 3)).astype(np.int32)
     capi.save_obj_mesh(str(p), v, f)
     assert p.read_text() == O.obj_text(v, f)
+    # the writer formats '%.4f' without printf except near rounding ties: values on and around the ties at the
+    # fourth decimal, signed zeros, tiny / huge / non-finite values, several chunks of 64 K lines (all threads)
+    n = 120000
+    k = rng.integers(-2_000_000, 2_000_000, n).astype(np.float64)
+    near = (k + 0.5) / 1e4 + rng.choice([0, 1e-12, -1e-12, 1e-9, -1e-9, 3e-7, -3e-7, 2e-6, -2e-6], n)
+    vals = np.concatenate([rng.standard_normal(n) * rng.choice([1e-6, 1e-3, 1, 100, 1e4, 1e6, 1e12], n), near,
+                           [0.0, -0.0, 1e5, -1e5, 99999.99995, -0.00004, -0.00005, 0.00005, np.inf, -np.inf, np.nan, 1e300, 5e-324,
+                            0.12345, 0.12355, 2.5e-5]])
+    v = np.concatenate([vals, np.zeros((-len(vals)) % 3)]).reshape(-1, 3)
+    f = np.array([[0, 1, 2], [2147483646, 0, 5], [7, 2147483646, 1]], dtype=np.int32)
+    capi.save_obj_mesh(str(p), v, f)
+    assert p.read_text() == O.obj_text(v, f)
 
 
 def test_product_never_imports_oracle():
