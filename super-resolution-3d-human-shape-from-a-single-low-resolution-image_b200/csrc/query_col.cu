@@ -33,9 +33,14 @@ using namespace col;
 
 // ring depths: P = 1 (one pass) 4 weight stages + 3 A slots; P = 3 (split operands) 3 + 4: a K block is a
 // (hi, lo) slot pair there, so four slots hold two K blocks
+// (measured at 512^3: 4 weight stages + 3 A slots 342 ms; 3 + 4 in the same shared memory 352 ms)
+#ifndef SURS_P1_NSTAGE
+#define SURS_P1_NSTAGE 4
+#define SURS_P1_NASLOT 3
+#endif
 template <int P> struct Ring {
-    static constexpr int NSTAGE = P == 1 ? 4 : 3;
-    static constexpr int NA_SLOT = P == 1 ? 3 : 4;
+    static constexpr int NSTAGE = P == 1 ? SURS_P1_NSTAGE : 3;
+    static constexpr int NA_SLOT = P == 1 ? SURS_P1_NASLOT : 4;
     static constexpr int AP = P == 1 ? 1 : 2;            // A blocks per K block (hi | hi, lo)
     static constexpr int WP = P == 1 ? 1 : 2;            // weight blocks per K block (hi | hi, lo)
     static constexpr int SMEM_W = 0;
@@ -188,6 +193,7 @@ struct EpiCtx {
     int row, hsel, lane;
     float zf, pred;
     uint32_t g;                    // running A-ring K block number
+    int ablate;                    // profiling builds only (SURS_COL_ABLATE): 8 no proxy fence, 16 no epilogue math / stores
     unsigned long long *prof;
 };
 
@@ -199,7 +205,7 @@ __device__ __forceinline__ uint32_t ring_acquire(EpiCtx &e)
 }
 __device__ __forceinline__ void ring_publish(EpiCtx &e, uint32_t slot, bool layer0 = false)   // layer0: the block feeds the second issuing thread too
 {
-    ptx::fence_proxy_async_smem();
+    if (!(e.ablate & 8)) ptx::fence_proxy_async_smem();
     __syncwarp();
     if (e.lane == 0) {
         ptx::mbar_arrive(&e.a_ready[slot]);
@@ -229,7 +235,8 @@ __device__ __forceinline__ void epilogue_256(EpiCtx &e, uint32_t taddr, int acc_
 #pragma unroll 1
         for (int part = 0; part < Ring<P>::AP; ++part) {       // P = 3: the K block goes out as a (hi, lo) slot pair
             const uint32_t slot = ring_acquire(e);
-            finish32<P, true, HAS_Z, HAS_P>(r[kb & 1], add + c, wz + c, wp + c, e.zf, e.pred, e.a_smem + slot * A_BLK_BYTES, e.row, e.hsel, part);
+            if (!(e.ablate & 16))
+                finish32<P, true, HAS_Z, HAS_P>(r[kb & 1], add + c, wz + c, wp + c, e.zf, e.pred, e.a_smem + slot * A_BLK_BYTES, e.row, e.hsel, part);
             ring_publish(e, slot);
         }
     }
@@ -296,6 +303,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
         EpiCtx e;
         e.a_ready = bars->a_ready; e.a_ready_b = bars->a_ready_b; e.a_free = bars->a_free; e.acc_free = bars->acc_free;
         e.nslot = NA_SLOT; e.a_smem = a_smem; e.lane = lane; e.prof = prof; e.g = 0;
+        e.ablate = PROF ? prm.ablate : 0;
         const int quarter = warp & 3;
         e.hsel = warp >> 2;
         e.row = quarter * 32 + lane;
