@@ -223,7 +223,9 @@ __device__ __forceinline__ void epilogue_256(EpiCtx &e, uint32_t taddr, int acc_
     ptx::tmem_ld32(taddr + e.hsel * 32, r[0]);
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
+        const long long t_a = e.prof ? clock64() : 0;
         ptx::tmem_ld_wait();
+        if (e.prof) atomicAdd(e.prof + 24, (unsigned long long)(clock64() - t_a));     // wait for the TMEM load
         if (kb < 3) {
             ptx::tmem_ld32(taddr + (kb + 1) * 64 + e.hsel * 32, r[(kb + 1) & 1]);
         } else {
@@ -235,9 +237,16 @@ __device__ __forceinline__ void epilogue_256(EpiCtx &e, uint32_t taddr, int acc_
 #pragma unroll 1
         for (int part = 0; part < Ring<P>::AP; ++part) {       // P = 3: the K block goes out as a (hi, lo) slot pair
             const uint32_t slot = ring_acquire(e);
+            const long long t_b = e.prof ? clock64() : 0;
             if (!(e.ablate & 16))
                 finish32<P, true, HAS_Z, HAS_P>(r[kb & 1], add + c, wz + c, wp + c, e.zf, e.pred, e.a_smem + slot * A_BLK_BYTES, e.row, e.hsel, part);
+            const long long t_c = e.prof ? clock64() : 0;
             ring_publish(e, slot);
+            if (e.prof) {
+                atomicAdd(e.prof + 25, (unsigned long long)(t_c - t_b));                   // bias / skip terms, leaky, fp16, stores
+                atomicAdd(e.prof + 26, (unsigned long long)(clock64() - t_c));             // fence + arrive
+                atomicAdd(e.prof + 27, 1ull);
+            }
         }
     }
 }
@@ -492,8 +501,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 ptx::tc_fence_after();
                 return slot;
             };
+            // a_free expects two arrivals (one per issuing thread in layer 1).  Where this thread is the only
+            // consumer the second arrival is a plain mbarrier arrive: a tcgen05.commit costs ~150 cycles of this
+            // thread's serial chain, and the phase still completes only when the commit's arrival lands
             auto release_a = [&](uint32_t slot, int commits) {
-                for (int c = 0; c < commits; ++c) ptx::umma_commit(&bars->a_free[slot]);
+                if (commits == 2) ptx::mbar_arrive(&bars->a_free[slot]);
+                ptx::umma_commit(&bars->a_free[slot]);
                 ++ablk;
             };
             // P = 3: one K block = A slots (hi, lo) x weight blocks (hi, lo): A_hi.W_hi, A_lo.W_hi, A_hi.W_lo --
@@ -1108,6 +1121,9 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
             (long long)prm.ntiles, grid, h[0] * k, h[11] * k, h[10] * k, h[20] * k, h[21] * k, h[22] * k, h[23] * k,
             h[30] * k, h[31] * k, h[33] * k, h[34] * k, h[35] * k, h[36] * k, h[40] * k, h[41] * k);
     fprintf(stderr, "[surs col profile] mma warp phases, kcycles/tile (both MLPs): wait acc_free + layer 1 %.1f | layer 2 %.1f | layer 3 %.1f\n", h[50] * k, h[51] * k, h[52] * k);
+    if (h[27])
+        fprintf(stderr, "[surs col profile] epilogue blocks of warp 0 (%.1f per tile), cycles per block: wait TMEM load %.0f | arithmetic + stores %.0f | fence + arrive %.0f\n",
+                (double)h[27] / prm.ntiles, (double)h[24] / h[27], (double)h[25] / h[27], (double)h[26] / h[27]);
     return 0;
 }
 
