@@ -35,10 +35,11 @@ enum {
     SURS_PREC_FP32 = 0,   /* CUDA-core fp32 FMA chain; agrees with the reference to ~1e-6     */
     SURS_PREC_FP16 = 1,   /* tcgen05 tensor cores, fp16 operands / fp32 accumulate (default)   */
     SURS_PREC_FP16X3 = 2  /* tensor cores with split operands: every product as A_hi.W_hi + A_lo.W_hi + A_hi.W_lo
-                           * (fp16 hi/lo pairs, fp32 accumulate), ~1e-5 from the reference at a third of the FP16
-                           * rate.  Column-factored grids only (surs_eval_grid / surs_eval_grid_octree without a
-                           * transform and with calib[0][2] == calib[1][2] == 0); every other point source runs
-                           * the SURS_PREC_FP32 kernel. */
+                           * (fp16 hi/lo pairs, fp32 accumulate), < 1e-4 from the reference's fp32 result.  Column-
+                           * factored grids (surs_eval_grid / surs_eval_grid_octree without a transform and with
+                           * calib[0][2] == calib[1][2] == 0) run at a third of the FP16 rate; every other point
+                           * source (surs_query, transformed grids, sheared calibrations) goes through per-point
+                           * tables on the same kernels (~45 M queries/s, 9x the SURS_PREC_FP32 kernel). */
 };
 
 #define SURS_NUM_LAYERS 5

@@ -61,6 +61,8 @@ static_assert(OFF_XW % 1024 == 0 && OFF_TABLE % 1024 == 0, "operand blocks must 
 
 // per-column table for planes [plane_lo, plane_lo + ncols / R1) -> ctx->col_table (query_col.cu)
 // passes: 1 = fp16 operands (SURS_PREC_FP16), 3 = split hi/lo operands (SURS_PREC_FP16X3)
-int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo, int64_t ncols, cudaStream_t st, int passes = 1);
+// point0 >= 0: point mode, row r = point point0 + r of io (R1 / plane_lo unused)
+int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo, int64_t ncols, cudaStream_t st, int passes = 1, int64_t point0 = -1);
+int surs_launch_query_generic_x3(surs_ctx *ctx, const PointIO &io, cudaStream_t st);
 int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int R2, cudaStream_t st, int passes = 1);
 int surs_launch_query_inc(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st);

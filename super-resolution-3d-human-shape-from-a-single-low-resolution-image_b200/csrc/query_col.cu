@@ -77,6 +77,7 @@ struct ColParams {
     int64_t ntiles;
     int nseg;                      // tiles per column = ceil(R2 / 128)
     int R1, R2, plane_lo;
+    int64_t n0, n_end;             // MODE 2: the launch covers points [n0, n_end) of io
     int ablate;                    // profiling only (SURS_COL_ABLATE): 1 = no weight traffic (results are garbage)
 };
 
@@ -263,13 +264,17 @@ __device__ unsigned long long g_col_prof[64];
 // accumulator it is reading.  So layer 1 runs as two sequential N halves into T0 (layer 0 is produced twice), layer 2
 // accumulates into T1 behind each half, layer 3 goes to T0 -- the accumulator being drained is never the one the
 // consumer of the drained blocks writes to.  One issuing thread; warp NEPI + 2 idles.
-template <bool PROF, bool INDEXED, int P>
+// MODE 0: dense slab; 1 (octree levels): rows = entries of io.idx_list, table rows = grid columns; 2 (arbitrary
+// point sources, SURS_PREC_FP16X3): rows = points prm.n0 + ..., the "column" table has one row PER POINT
+// (col_table_kernel in point mode), so nothing is shared between rows but the kernels and their arithmetic are reused.
+template <bool PROF, int MODE, int P>
 __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_constant__ PointIO io, const __grid_constant__ ColParams prm)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - raw);
+    constexpr bool INDEXED = MODE != 0;
     using RG = Ring<P>;
     constexpr int NSTAGE = RG::NSTAGE, NA_SLOT = RG::NA_SLOT, AP = RG::AP;
     constexpr int SMEM_W = RG::SMEM_W, SMEM_A = RG::SMEM_A, SMEM_CV = RG::SMEM_CV, SMEM_GV = RG::SMEM_GV;
@@ -343,19 +348,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 cv = cv_s + cvb * CV_FLOATS;
             } else {
                 auto node = [&](int64_t n, int64_t &c, Projected &q) {
+                    if (MODE == 2) {
+                        const int64_t nn = n < prm.n_end ? n : prm.n_end - 1;
+                        float x, y, z;
+                        pointio_load(io, nn, x, y, z);
+                        q = project_point(io, x, y, z);
+                        c = nn - prm.n0;
+                        return;
+                    }
                     const int64_t lin = io.idx_list[n < io.n ? n : io.n - 1];
                     c = lin / prm.R2;
                     const int kk = (int)(lin - c * prm.R2), jj = (int)(c % prm.R1), ii = (int)(c / prm.R1);
                     q = project_point(io, (float)io.axis[0][ii], (float)io.axis[1][jj], (float)io.axis[2][kk]);
                 };
-                n_own = tile * TILE_M + e.row;
+                const int64_t nbase = MODE == 2 ? prm.n0 : 0;
+                n_own = nbase + tile * TILE_M + e.row;
                 node(n_own, col, pr);
                 cv = prm.table + col * CV_ROW_FLOATS;               // this row's column vectors, in global memory
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     int64_t c;
                     Projected q;
-                    node(tile * TILE_M + lane + 32 * r, c, q);
+                    node(nbase + tile * TILE_M + lane + 32 * r, c, q);
                     zf4[r] = q.zf;
                     trow4[r] = prm.table + c * CV_ROW_FLOATS;
                 }
@@ -456,7 +470,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                         pred_lr = pred;
                         pred_x[e.row] = pred;
                     } else if (INDEXED) {
-                        if (n_own < io.n) pointio_store(io, n_own, pred, pred_lr);
+                        if (n_own < (MODE == 2 ? prm.n_end : io.n)) pointio_store(io, n_own, pred, pred_lr);
                     } else if (k < prm.R2) {
                         const int64_t n = col * prm.R2 + k;
                         io.out_hr[n] = pred;
@@ -702,6 +716,7 @@ struct TbParams {
     FeatMaps fm;
     float *table;
     int64_t ncols;
+    int64_t point0;                // >= 0: point mode -- table row r belongs to point point0 + r of io (any point source)
     int R1, plane_lo;
 };
 
@@ -729,6 +744,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
     ptx::tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
     const int64_t ntiles = (prm.ncols + TILE_M - 1) / TILE_M;
+    // the C1 block (layer 1 of the all-negative state) only serves query_inc.cu on dense grids: not computed in point mode
+    const bool skip_c1 = prm.point0 >= 0;
 
     if (warp < 4) {
         const int row = warp * 32 + lane;
@@ -737,8 +754,15 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
             int64_t col = tile * TILE_M + row;
             const bool valid = col < prm.ncols;
             if (!valid) col = prm.ncols - 1;
-            const int i = prm.plane_lo + (int)(col / prm.R1), j = (int)(col % prm.R1);
-            const Projected pr = project_point(io, (float)io.axis[0][i], (float)io.axis[1][j], (float)io.axis[2][0]);
+            Projected pr;
+            if (prm.point0 >= 0) {
+                float x, y, z;
+                pointio_load(io, prm.point0 + col, x, y, z);
+                pr = project_point(io, x, y, z);
+            } else {
+                const int i = prm.plane_lo + (int)(col / prm.R1), j = (int)(col % prm.R1);
+                pr = project_point(io, (float)io.axis[0][i], (float)io.axis[1][j], (float)io.axis[2][0]);
+            }
             if (P == 1) gather_rows<32>(prm.fm, pr, warp * 32, lane, f_smem);
             else gather_rows_x3<32>(prm.fm, pr, warp * 32, lane, f_smem);
             ptx::fence_proxy_async_smem();
@@ -748,6 +772,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
 #pragma unroll 1
             for (int ch = 0; ch < TB_CHUNKS; ++ch) {
                 const int m = ch / TB_CHUNKS_PER_MLP, cc = ch % TB_CHUNKS_PER_MLP, t = ch & 1;
+                if (skip_c1 && (cc == 4 || cc == 5)) continue;       // an (even, odd) chunk pair: accumulator parity is kept
                 ptx::mbar_wait(&bars->acc_full[t], acc[t] & 1u, 70);
                 ptx::tc_fence_after();
                 const uint32_t taddr = tmem + t * 256 + ((uint32_t)(warp * 32) << 16);
@@ -795,6 +820,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
                 ptx::tc_fence_after();
                 for (int ch = 0; ch < TB_CHUNKS; ++ch) {
                     const int t = ch & 1;
+                    if (skip_c1 && (ch % TB_CHUNKS_PER_MLP == 4 || ch % TB_CHUNKS_PER_MLP == 5)) continue;
                     ptx::mbar_wait(&bars->acc_free[t], (acc[t] & 1u) ^ 1u, 72);
                     ptx::tc_fence_after();
                     for (int kp = 0; kp < 5 * P; ++kp) {
@@ -820,6 +846,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
                 for (int ch = 0; ch < TB_CHUNKS; ++ch)
                     for (int kp = 0; kp < 5 * P; ++kp) {
                         const uint32_t bytes = (ch % TB_CHUNKS_PER_MLP) == 7 ? W3_BLK_BYTES : W_BLK_BYTES;
+                        if (skip_c1 && (ch % TB_CHUNKS_PER_MLP == 4 || ch % TB_CHUNKS_PER_MLP == 5)) { src += bytes; continue; }
                         const uint32_t s = wblk % NST;
                         ptx::mbar_wait(&bars->empty_w[s], ((wblk / NST) & 1u) ^ 1u, 74);
                         ptx::mbar_arrive_expect_tx(&bars->full_w[s], bytes);
@@ -1050,7 +1077,7 @@ int surs_col_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS
     return 0;
 }
 
-int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo, int64_t ncols, cudaStream_t st, int passes)
+int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo, int64_t ncols, cudaStream_t st, int passes, int64_t point0)
 {
     if (surs_ensure(ctx, (void **)&ctx->col_table, &ctx->col_table_cap, (size_t)ncols * CV_ROW_BYTES)) return 1;
     uint8_t *base = (uint8_t *)ctx->col_weights;
@@ -1064,6 +1091,7 @@ int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo,
     tb.fm.H_lr = ctx->H_lr; tb.fm.W_lr = ctx->W_lr; tb.fm.H_hr = ctx->H_hr; tb.fm.W_hr = ctx->W_hr;
     tb.table = (float *)ctx->col_table;
     tb.ncols = ncols; tb.R1 = R1; tb.plane_lo = plane_lo;
+    tb.point0 = point0;
     const int64_t tb_tiles = (ncols + TILE_M - 1) / TILE_M;
     const int tb_grid = (int)(tb_tiles < ctx->sm_count ? tb_tiles : ctx->sm_count);
     if (passes == 3) {
@@ -1093,25 +1121,26 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
     prm.nseg = (R2 + TILE_M - 1) / TILE_M;
     prm.ntiles = ncols * prm.nseg;
     prm.R1 = R1; prm.R2 = R2; prm.plane_lo = plane_lo;
+    prm.n0 = 0; prm.n_end = 0;
     prm.ablate = getenv("SURS_COL_ABLATE") ? atoi(getenv("SURS_COL_ABLATE")) : 0;
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
     static const bool profile = getenv("SURS_TC_PROFILE") != nullptr;
     if (passes == 3) {
-        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<3>::SMEM_TOTAL));
-        query_col_kernel<false, false, 3><<<grid, NTHREADS, Ring<3>::SMEM_TOTAL, st>>>(io, prm);
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<3>::SMEM_TOTAL));
+        query_col_kernel<false, 0, 3><<<grid, NTHREADS, Ring<3>::SMEM_TOTAL, st>>>(io, prm);
         SURS_LAUNCH_CHECK(ctx, "query_col_kernel<x3>");
         return 0;
     }
     if (!profile) {
-        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<1>::SMEM_TOTAL));
-        query_col_kernel<false, false, 1><<<grid, NTHREADS, Ring<1>::SMEM_TOTAL, st>>>(io, prm);
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<1>::SMEM_TOTAL));
+        query_col_kernel<false, 0, 1><<<grid, NTHREADS, Ring<1>::SMEM_TOTAL, st>>>(io, prm);
         SURS_LAUNCH_CHECK(ctx, "query_col_kernel");
         return 0;
     }
     unsigned long long zero[64] = {0}, h[64];
     SURS_CUDA(ctx, cudaMemcpyToSymbol(g_col_prof, zero, sizeof(zero)));
-    SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<1>::SMEM_TOTAL));
-    query_col_kernel<true, false, 1><<<grid, NTHREADS, Ring<1>::SMEM_TOTAL, st>>>(io, prm);
+    SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<true, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<1>::SMEM_TOTAL));
+    query_col_kernel<true, 0, 1><<<grid, NTHREADS, Ring<1>::SMEM_TOTAL, st>>>(io, prm);
     SURS_LAUNCH_CHECK(ctx, "query_col_kernel<profile>");
     SURS_CUDA(ctx, cudaStreamSynchronize(st));
     SURS_CUDA(ctx, cudaMemcpyFromSymbol(h, g_col_prof, sizeof(h)));
@@ -1141,15 +1170,45 @@ int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int 
     prm.nseg = 1;
     prm.ntiles = (io.n + TILE_M - 1) / TILE_M;
     prm.R1 = R1; prm.R2 = R2; prm.plane_lo = 0;
+    prm.n0 = 0; prm.n_end = 0;
     prm.ablate = 0;
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
     if (passes == 3) {
-        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<3>::SMEM_TOTAL));
-        query_col_kernel<false, true, 3><<<grid, NTHREADS, Ring<3>::SMEM_TOTAL, st>>>(io, prm);
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<3>::SMEM_TOTAL));
+        query_col_kernel<false, 1, 3><<<grid, NTHREADS, Ring<3>::SMEM_TOTAL, st>>>(io, prm);
     } else {
-        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<1>::SMEM_TOTAL));
-        query_col_kernel<false, true, 1><<<grid, NTHREADS, Ring<1>::SMEM_TOTAL, st>>>(io, prm);
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<1>::SMEM_TOTAL));
+        query_col_kernel<false, 1, 1><<<grid, NTHREADS, Ring<1>::SMEM_TOTAL, st>>>(io, prm);
     }
     SURS_LAUNCH_CHECK(ctx, "query_col_kernel<indexed>");
+    return 0;
+}
+
+// SURS_PREC_FP16X3 for point sources without a column structure (explicit points, transformed grids, sheared
+// calibrations, octree lists of such grids): chunks of 128 K points; per chunk the table kernel computes the
+// W.f products of every POINT (split operands) and query_col_kernel<MODE 2> runs layers 0-4 on them.  15.4 KB of
+// table per point make this path HBM-heavy (30 KB per point written and read back), still ~10x the CUDA-core mode.
+int surs_launch_query_generic_x3(surs_ctx *ctx, const PointIO &io, cudaStream_t st)
+{
+    if (io.n <= 0) return 0;
+    const int64_t CH = 131072;
+    uint8_t *base = (uint8_t *)ctx->col_weights;
+    for (int64_t s0 = 0; s0 < io.n; s0 += CH) {
+        const int64_t len = io.n - s0 < CH ? io.n - s0 : CH;
+        if (surs_col_build_table(ctx, io, 1, 0, len, st, 3, s0)) return 1;
+        ColParams prm;
+        prm.weights = (const uint8_t *)ctx->col_weights_x3;
+        prm.gv = reinterpret_cast<const float *>(base + OFF_GV);
+        prm.table = (const float *)ctx->col_table;
+        prm.nseg = 1;
+        prm.ntiles = (len + TILE_M - 1) / TILE_M;
+        prm.R1 = 1; prm.R2 = 1; prm.plane_lo = 0;
+        prm.n0 = s0; prm.n_end = s0 + len;
+        prm.ablate = 0;
+        const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
+        SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<3>::SMEM_TOTAL));
+        query_col_kernel<false, 2, 3><<<grid, NTHREADS, Ring<3>::SMEM_TOTAL, st>>>(io, prm);
+        SURS_LAUNCH_CHECK(ctx, "query_col_kernel<points, x3>");
+    }
     return 0;
 }

@@ -205,8 +205,8 @@ static int check_ready(surs_ctx *ctx, int precision)
 
 static int run_query(surs_ctx *ctx, const PointIO &io, int precision, cudaStream_t st)
 {
-    // SURS_PREC_FP16X3 has tensor-core kernels for column-factored grids only (query_col.cu); every other point
-    // source runs the exact CUDA-core kernel, which is the more accurate of the two
+    // SURS_PREC_FP16X3 without a column structure: per-point tables through the column kernels (query_col.cu)
+    if (precision == SURS_PREC_FP16X3) return surs_launch_query_generic_x3(ctx, io, st);
     return precision == SURS_PREC_FP16 ? surs_launch_query_tc(ctx, io, st) : surs_launch_query_simt(ctx, io, st);
 }
 

@@ -340,11 +340,36 @@ def test_split_operand_mode_dense_and_octree(ctx, case32):
     err = max(np.abs(x3[0].cpu().numpy().reshape(-1) - ohr).max(), np.abs(x3[1].cpu().numpy().reshape(-1) - olr).max())
     print("split-operand path vs float64 oracle: max|d| %.3g" % err)
     assert err < TOL_X3_MAX
-    # point sources without a column structure run the exact CUDA-core kernel in this mode
-    p = torch.from_numpy(pts).to(ctx.device)
-    a = ctx.query(p, case32.calib, *znum(case32), precision=_capi.PREC_FP16X3)
-    b = ctx.query(p, case32.calib, *znum(case32), precision=_capi.PREC_FP32)
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # point sources without a column structure (explicit points incl. out-of-image ones and ragged counts, transformed
+    # grids, octree lists of a transformed grid, a calibration with shear): per-point tables through the same kernels
+    for n in (1, 127, 129, 5000, 140000):
+        p = torch.from_numpy(syn.random_points(n, seed=n, lo=-0.55, hi=0.55)).to(ctx.device)
+        a = ctx.query(p, case32.calib, *znum(case32), precision=_capi.PREC_FP16X3)
+        b = ctx.query(p, case32.calib, *znum(case32), precision=_capi.PREC_FP32)
+        err = max((a[0] - b[0]).abs().max().item(), (a[1] - b[1]).abs().max().item())
+        print("split-operand point query n=%d: max|d| vs fp32 %.3g" % (n, err))
+        assert err < TOL_X3_MAX
+        assert np.array_equal((a[0] == 0).cpu().numpy(), (b[0] == 0).cpu().numpy())
+    T = np.array([[0.9, 0.1, 0.0, 0.01], [-0.1, 0.9, 0.05, -0.02], [0.0, -0.05, 1.1, 0.03], [0, 0, 0, 1.0]])
+    args = ((64, 64, 64), [-0.5] * 3, [0.5] * 3, case32.calib) + znum(case32)
+    a = ctx.eval_grid(*args, transform=T, precision=_capi.PREC_FP16X3)
+    b = ctx.eval_grid(*args, transform=T, precision=_capi.PREC_FP32)
+    assert max((a[0] - b[0]).abs().max().item(), (a[1] - b[1]).abs().max().item()) < TOL_X3_MAX
+    oa = ctx.eval_grid_octree(*args, threshold=0.05, init_resolution=16, transform=T, precision=_capi.PREC_FP16X3)
+    coords, _ = O.create_grid(64, 64, 64, np.array([-0.5] * 3), np.array([0.5] * 3), transform=T)
+
+    def eval_func(points):                                   # the same per-point arithmetic through surs_query
+        q = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float32)).to(ctx.device)
+        u, v = ctx.query(q, case32.calib, *znum(case32), precision=_capi.PREC_FP16X3)
+        return u.cpu().numpy(), v.cpu().numpy()
+    ohr, olr = O.eval_grid_octree(0.05, coords, eval_func, init_resolution=16, num_samples=50000)
+    assert oa[2] < 64 ** 3 and np.array_equal(oa[0].cpu().numpy(), ohr) and np.array_equal(oa[1].cpu().numpy(), olr)
+    shear = case32.calib.copy()
+    shear[0, 2] = 0.05
+    p = torch.from_numpy(syn.random_points(3000, seed=3, lo=-0.5, hi=0.5)).to(ctx.device)
+    a = ctx.query(p, shear, *znum(case32), precision=_capi.PREC_FP16X3)
+    b = ctx.query(p, shear, *znum(case32), precision=_capi.PREC_FP32)
+    assert max((a[0] - b[0]).abs().max().item(), (a[1] - b[1]).abs().max().item()) < TOL_X3_MAX
 
 
 def test_incremental_layer1_dense_path(ctx, case32, monkeypatch):
