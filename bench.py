@@ -298,6 +298,30 @@ def run_ours(args):
                "s_per_mesh": dt, "verts_hr": int(r[0].shape[0]), "faces_hr": int(r[1].shape[0]),
                "verts_lr": int(r[4].shape[0]), "faces_lr": int(r[5].shape[0])}
 
+    if world > 1 and not args.no_e2e:
+        # N > 1: the host-facing distributed call -- every rank uploads the feature maps from pinned host memory,
+        # reconstructs its slab, the meshes are gathered on rank 0 and copied to host numpy
+        def e2e_step_n():
+            return parallel.reconstruction_from_host(ctx, f_lr_host, f_hr_host, (res, res, res), b_min, b_max, case.calib, zn, zd,
+                                                     mat[:3, :4], precision=prec)
+        for _ in range(3):
+            r = e2e_step_n()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(n_e2e):
+            r = e2e_step_n()
+        barrier()
+        te = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dt = float(te.item())
+        if rank == 0:
+            e2e = {"value": n_queries / dt, "unit": "queries/s",
+                   "h2d_bytes_per_step": int(world * (f_lr_host.numel() * 4 + f_hr_host.numel() * 4)),
+                   "d2h_bytes_per_step": sum(int(a.nbytes) for a in r), "s_per_mesh": dt,
+                   "note": "every rank uploads both feature maps (h2d is the sum over ranks); meshes gathered over NCCL, host copy on rank 0",
+                   "verts_hr": int(r[0].shape[0]), "faces_hr": int(r[1].shape[0]), "verts_lr": int(r[4].shape[0]), "faces_lr": int(r[5].shape[0])}
+
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -207,3 +207,18 @@ def reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, transform
         g = got[per * k:per * (k + 1)]
         results.append((g[0], g[1], g[2], g[3]) if want_normals else (g[0], g[1], None, None))
     return tuple(results)
+
+
+def reconstruction_from_host(ctx, feat_lr_host, feat_hr_host, res, b_min, b_max, calib, z_num, z_den, mat,
+                             precision=_capi.PREC_FP16, group=None):
+    """The host-facing multi-GPU call: every rank uploads the two encoder feature maps (NCHW fp32 host tensors,
+    ideally pinned) to its GPU, reconstructs its slab, and rank 0 returns the reference's 8-tuple
+    (lib/mesh_util.py:8-49: verts float64 world coordinates, faces int32, normals, values -- HR then LR) as host
+    numpy arrays; the other ranks return None."""
+    from .lib.mesh_util import _to_host
+    dev = ctx.device
+    ctx.set_features(feat_lr_host.to(dev, non_blocking=True), feat_hr_host.to(dev, non_blocking=True))
+    hr, lr = reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, precision=precision, group=group)
+    if hr is None:
+        return None
+    return tuple(_to_host(list(hr) + list(lr)))
