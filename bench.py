@@ -315,11 +315,13 @@ def run_ours(args):
         te = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dt = float(te.item())
+        up = torch.tensor([ctx.last_upload_bytes], device=dev, dtype=torch.int64)
+        dist.all_reduce(up)
         if rank == 0:
             e2e = {"value": n_queries / dt, "unit": "queries/s",
-                   "h2d_bytes_per_step": int(world * (f_lr_host.numel() * 4 + f_hr_host.numel() * 4)),
+                   "h2d_bytes_per_step": int(up.item()),
                    "d2h_bytes_per_step": sum(int(a.nbytes) for a in r), "s_per_mesh": dt,
-                   "note": "every rank uploads both feature maps (h2d is the sum over ranks); meshes gathered over NCCL, host copy on rank 0",
+                   "note": "every rank uploads the stripe of the two feature maps its slab samples (h2d = sum over ranks); meshes gathered over NCCL, host copy on rank 0",
                    "verts_hr": int(r[0].shape[0]), "faces_hr": int(r[1].shape[0]), "verts_lr": int(r[4].shape[0]), "faces_lr": int(r[5].shape[0])}
 
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------

@@ -73,6 +73,15 @@ int surs_set_weights(surs_ctx *ctx,
 int surs_set_features(surs_ctx *ctx, const float *f_lr, int C_lr, int H_lr, int W_lr,
                       const float *f_hr, int C_hr, int H_hr, int W_hr, void *stream);
 
+/* Same maps from HOST memory (NCHW fp32; pinned memory makes the copies asynchronous), restricted to what a
+ * caller that only samples image coordinates u in [u_lo, u_hi] needs: the pixel columns grid_sample touches for
+ * that range (+ one pixel) are uploaded with one strided copy per map and repacked; the rest of the resident maps
+ * is left as it was.  A slab-parallel rank (axis 0 = world x, u = calib[0][0] x + ...) uploads 1/N of the
+ * 80-320 MiB this way.  Calls that would sample outside the covered range return an error (surs_query and
+ * surs_eval_grid_octree need whole maps; surs_eval_grid checks its slab's range).  u_lo <= -1 and u_hi >= 1: whole maps. */
+int surs_set_features_host(surs_ctx *ctx, const float *f_lr, int C_lr, int H_lr, int W_lr,
+                           const float *f_hr, int C_hr, int H_hr, int W_hr, float u_lo, float u_hi, void *stream);
+
 /* Replaces: SuRSNet.query_mr + query_sr + get_preds (lib/model/SuRSNet.py:131-187,
  * lib/model/BaseSuRSNet.py:80-85) with lib/geometry.py:15-31 `orthogonal`, :4-12 `index`,
  * lib/model/DepthNormalizer.py:18 and lib/model/SurfaceClassifier.py:45-81 fused.

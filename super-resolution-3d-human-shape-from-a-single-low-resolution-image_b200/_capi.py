@@ -35,6 +35,8 @@ SIGNATURES = {
     "surs_set_weights": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int, _P]),
     "surs_set_features": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
+    "surs_set_features_host": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, _P]),
     "surs_query": (ctypes.c_int, [_P, _P, _I64, _P, ctypes.c_float, ctypes.c_float, ctypes.c_int, _P, _P, _P]),
     "surs_query_host": (ctypes.c_int, [_P, _P, _I64, _P, ctypes.c_float, ctypes.c_float, ctypes.c_int, _P, _P, _P]),
     "surs_eval_grid": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_int,
@@ -163,6 +165,31 @@ class Context:
             torch.cuda.current_stream(self.device).synchronize()   # inputs are borrowed until the repack ran
 
     # ---- query ----------------------------------------------------------------------
+    def set_features_host(self, f_lr, f_hr, u_range=None):
+        """Feature maps from HOST tensors (NCHW fp32, ideally pinned).  u_range = (u_lo, u_hi): upload only the pixel
+        columns that image coordinates in that range sample (slab-parallel ranks); None: the whole maps."""
+        f_lr = f_lr.detach().to(torch.float32).contiguous()
+        f_hr = f_hr.detach().to(torch.float32).contiguous()
+        if f_lr.is_cuda or f_hr.is_cuda:
+            raise RuntimeError("set_features_host takes host tensors; use set_features for device tensors")
+        if f_lr.dim() == 4:
+            if f_lr.shape[0] != 1 or f_hr.shape[0] != 1:
+                raise RuntimeError("surs_b200 kernels handle one view (num_views == 1)")
+            f_lr, f_hr = f_lr[0], f_hr[0]
+        u_lo, u_hi = (-1.0, 1.0) if u_range is None else (float(u_range[0]), float(u_range[1]))
+
+        def stripe_bytes(f):                              # same pixel-column rule as stripe_columns() in csrc/surs_api.cu
+            W = f.shape[2]
+            x0 = max(0, int(np.floor((min(max(u_lo, -1.0), 1.0) + 1.0) * 0.5 * (W - 1))) - 1)
+            x1 = min(W, int(np.floor((min(max(u_hi, -1.0), 1.0) + 1.0) * 0.5 * (W - 1))) + 3)
+            return 4 * f.shape[0] * f.shape[1] * max(0, x1 - x0)
+        self.last_upload_bytes = stripe_bytes(f_lr) + stripe_bytes(f_hr)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.surs_set_features_host(self._h, _ptr(f_lr), f_lr.shape[0], f_lr.shape[1], f_lr.shape[2],
+                                                        _ptr(f_hr), f_hr.shape[0], f_hr.shape[1], f_hr.shape[2], u_lo, u_hi,
+                                                        _stream(self.device)))
+            torch.cuda.current_stream(self.device).synchronize()   # the host buffers are borrowed until the copies ran
+
     def query(self, points, calib, z_num, z_den, precision=PREC_FP16):
         """points [3,N] fp32 on the device -> (pred_hr, pred_lr) fp32 [N] device tensors."""
         pts = points.detach().to(self.device, torch.float32).contiguous()

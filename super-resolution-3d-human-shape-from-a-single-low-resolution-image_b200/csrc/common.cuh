@@ -143,6 +143,9 @@ struct surs_ctx {
     float *f_lr32, *f_hr32;                // [H][W][C] fp32
     __half *f_lr16, *f_hr16;               // [H][W][C] fp16
     size_t f_lr_cap, f_hr_cap;
+    float feat_u_lo, feat_u_hi;            // image-coordinate range covered by the resident maps ([-1, 1] = whole maps)
+    void *feat_stage;                      // NCHW stripe staging of surs_set_features_host
+    size_t feat_stage_cap;
     // ---- grid scratch -----------------------------------------------------------
     double *axis_dev;                      // 3 per-axis coordinate tables
     size_t axis_cap;

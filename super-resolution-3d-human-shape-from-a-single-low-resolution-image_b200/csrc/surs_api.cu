@@ -73,7 +73,7 @@ extern "C" void surs_destroy(surs_ctx *ctx)
     cudaFree(ctx->col_weights);
     cudaFree(ctx->col_weights_x3);
     cudaFree(ctx->col_table);
-    cudaFree(ctx->f_lr32); cudaFree(ctx->f_hr32); cudaFree(ctx->f_lr16); cudaFree(ctx->f_hr16);
+    cudaFree(ctx->f_lr32); cudaFree(ctx->f_hr32); cudaFree(ctx->f_lr16); cudaFree(ctx->f_hr16); cudaFree(ctx->feat_stage);
     cudaFree(ctx->axis_dev); cudaFree(ctx->dirty); cudaFree(ctx->idx_list); cudaFree(ctx->counter);
     cudaFree(ctx->stage_pts); cudaFree(ctx->stage_out);
     cudaFree(ctx->mc_block_tot); cudaFree(ctx->mc_bits); cudaFree(ctx->mc_cell_tot); cudaFree(ctx->mc_cells); cudaFree(ctx->mc_vid); cudaFree(ctx->mc_tables);
@@ -159,15 +159,11 @@ __global__ void repack_kernel(const float *__restrict__ src, float *__restrict__
         }
 }
 
-extern "C" int surs_set_features(surs_ctx *ctx, const float *f_lr, int C_lr, int H_lr, int W_lr,
-                                 const float *f_hr, int C_hr, int H_hr, int W_hr, void *stream)
+static int ensure_feature_maps(surs_ctx *ctx, int C_lr, int H_lr, int W_lr, int C_hr, int H_hr, int W_hr, bool have_ptrs)
 {
-    if (!ctx) return 1;
-    cudaStream_t st = (cudaStream_t)stream;
-    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (C_lr != SURS_C_LR || C_hr != SURS_C_HR)
         SURS_FAIL(ctx, "surs_set_features: expected %d + %d channels, got %d + %d", SURS_C_LR, SURS_C_HR, C_lr, C_hr);
-    if (H_lr < 2 || W_lr < 2 || H_hr < 2 || W_hr < 2 || !f_lr || !f_hr)
+    if (H_lr < 2 || W_lr < 2 || H_hr < 2 || W_hr < 2 || !have_ptrs)
         SURS_FAIL(ctx, "surs_set_features: bad feature map shape");
     const size_t n_lr = (size_t)H_lr * W_lr * C_lr, n_hr = (size_t)H_hr * W_hr * C_hr;
     if (n_lr > ctx->f_lr_cap) {
@@ -182,12 +178,95 @@ extern "C" int surs_set_features(surs_ctx *ctx, const float *f_lr, int C_lr, int
         SURS_CUDA(ctx, cudaMalloc(&ctx->f_hr16, n_hr * sizeof(__half)));
         ctx->f_hr_cap = n_hr;
     }
+    return 0;
+}
+
+extern "C" int surs_set_features(surs_ctx *ctx, const float *f_lr, int C_lr, int H_lr, int W_lr,
+                                 const float *f_hr, int C_hr, int H_hr, int W_hr, void *stream)
+{
+    if (!ctx) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ensure_feature_maps(ctx, C_lr, H_lr, W_lr, C_hr, H_hr, W_hr, f_lr && f_hr)) return 1;
     dim3 block(32, 8);
     repack_kernel<<<dim3((H_lr * W_lr + 31) / 32, C_lr / 32), block, 0, st>>>(f_lr, ctx->f_lr32, ctx->f_lr16, C_lr, H_lr * W_lr);
     SURS_LAUNCH_CHECK(ctx, "repack_kernel(lr)");
     repack_kernel<<<dim3((H_hr * W_hr + 31) / 32, C_hr / 32), block, 0, st>>>(f_hr, ctx->f_hr32, ctx->f_hr16, C_hr, H_hr * W_hr);
     SURS_LAUNCH_CHECK(ctx, "repack_kernel(hr)");
     ctx->H_lr = H_lr; ctx->W_lr = W_lr; ctx->H_hr = H_hr; ctx->W_hr = W_hr;
+    ctx->feat_u_lo = -1.0f; ctx->feat_u_hi = 1.0f;
+    ctx->have_features = 1;
+    return 0;
+}
+
+// NCHW fp32 stripe [C][H][Ws] (pixel columns x0 .. x0 + Ws - 1 of a W-wide map) -> the same columns of the
+// channels-last maps; every other pixel of the maps keeps whatever it held.
+__global__ void repack_stripe_kernel(const float *__restrict__ src, float *__restrict__ dst32, __half *__restrict__ dst16,
+                                     int C, int H, int W, int x0, int Ws)
+{
+    __shared__ float tile[32][33];
+    const int HWs = H * Ws;
+    int px = blockIdx.x * 32 + threadIdx.x, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8)
+        if (c0 + i < C && px < HWs) tile[i][threadIdx.x] = src[(size_t)(c0 + i) * HWs + px];
+    __syncthreads();
+    int c = c0 + threadIdx.x, p0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int p = p0 + i;
+        if (p < HWs && c < C) {
+            const int y = p / Ws, xs = p - y * Ws;
+            const size_t o = ((size_t)y * W + x0 + xs) * C + c;
+            const float v = tile[threadIdx.x][i];
+            dst32[o] = v;
+            dst16[o] = __float2half_rn(v);
+        }
+    }
+}
+
+// pixel columns touched by grid_sample(align_corners=True) for u in [u_lo, u_hi] (lib/geometry.py:11), one pixel of margin
+static void stripe_columns(float u_lo, float u_hi, int W, int *x0, int *x1)
+{
+    const float a = (fminf(fmaxf(u_lo, -1.0f), 1.0f) + 1.0f) * 0.5f * (float)(W - 1);
+    const float b = (fminf(fmaxf(u_hi, -1.0f), 1.0f) + 1.0f) * 0.5f * (float)(W - 1);
+    int lo = (int)floorf(a) - 1, hi = (int)floorf(b) + 3;            // [lo, hi)
+    *x0 = lo < 0 ? 0 : lo;
+    *x1 = hi > W ? W : hi;
+}
+
+extern "C" int surs_set_features_host(surs_ctx *ctx, const float *f_lr, int C_lr, int H_lr, int W_lr,
+                                      const float *f_hr, int C_hr, int H_hr, int W_hr, float u_lo, float u_hi, void *stream)
+{
+    if (!ctx) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!(u_lo <= u_hi)) SURS_FAIL(ctx, "surs_set_features_host: empty u range");
+    if (ensure_feature_maps(ctx, C_lr, H_lr, W_lr, C_hr, H_hr, W_hr, f_lr && f_hr)) return 1;
+    const float *src[2] = {f_lr, f_hr};
+    const int C[2] = {C_lr, C_hr}, H[2] = {H_lr, H_hr}, W[2] = {W_lr, W_hr};
+    float *d32[2] = {ctx->f_lr32, ctx->f_hr32};
+    __half *d16[2] = {ctx->f_lr16, ctx->f_hr16};
+    size_t need = 0;
+    for (int k = 0; k < 2; ++k) {
+        int x0, x1;
+        stripe_columns(u_lo, u_hi, W[k], &x0, &x1);
+        const size_t bytes = x1 > x0 ? (size_t)C[k] * H[k] * (x1 - x0) * sizeof(float) : 0;
+        need = bytes > need ? bytes : need;
+    }
+    if (surs_ensure(ctx, (void **)&ctx->feat_stage, &ctx->feat_stage_cap, need)) return 1;
+    for (int k = 0; k < 2; ++k) {
+        int x0, x1;
+        stripe_columns(u_lo, u_hi, W[k], &x0, &x1);
+        const int Ws = x1 - x0;
+        if (Ws <= 0) continue;
+        // rows of Ws floats out of rows of W floats: one strided copy for all C * H rows (pinned source: asynchronous)
+        SURS_CUDA(ctx, cudaMemcpy2DAsync(ctx->feat_stage, (size_t)Ws * sizeof(float), src[k] + x0, (size_t)W[k] * sizeof(float),
+                                         (size_t)Ws * sizeof(float), (size_t)C[k] * H[k], cudaMemcpyHostToDevice, st));
+        repack_stripe_kernel<<<dim3((H[k] * Ws + 31) / 32, C[k] / 32), dim3(32, 8), 0, st>>>((const float *)ctx->feat_stage, d32[k], d16[k], C[k], H[k], W[k], x0, Ws);
+        SURS_LAUNCH_CHECK(ctx, "repack_stripe_kernel");
+    }
+    ctx->H_lr = H_lr; ctx->W_lr = W_lr; ctx->H_hr = H_hr; ctx->W_hr = W_hr;
+    ctx->feat_u_lo = u_lo <= -1.0f ? -1.0f : u_lo;
+    ctx->feat_u_hi = u_hi >= 1.0f ? 1.0f : u_hi;
     ctx->have_features = 1;
     return 0;
 }
@@ -195,10 +274,16 @@ extern "C" int surs_set_features(surs_ctx *ctx, const float *f_lr, int C_lr, int
 // ------------------------------------------------------------------------------------
 // query
 // ------------------------------------------------------------------------------------
-static int check_ready(surs_ctx *ctx, int precision)
+// u_lo / u_hi: the range of image coordinates u the call will sample; the resident features must cover it
+// (surs_set_features_host may have uploaded a stripe of pixel columns only)
+static int check_ready(surs_ctx *ctx, int precision, float u_lo = -1.0f, float u_hi = 1.0f)
 {
     if (!ctx->have_weights) SURS_FAIL(ctx, "surs_set_weights has not been called");
     if (!ctx->have_features) SURS_FAIL(ctx, "surs_set_features has not been called");
+    // (the stripe carries a pixel of margin, > 1e-3 in u for any map below 2000 pixels: 1e-4 of slack is safe)
+    if (fmaxf(u_lo, -1.0f) < ctx->feat_u_lo - 1e-4f || fminf(u_hi, 1.0f) > ctx->feat_u_hi + 1e-4f)
+        SURS_FAIL(ctx, "the resident feature maps cover u in [%g, %g] only (surs_set_features_host stripe); this call samples [%g, %g]",
+                  ctx->feat_u_lo, ctx->feat_u_hi, u_lo, u_hi);
     if (precision != SURS_PREC_FP32 && precision != SURS_PREC_FP16 && precision != SURS_PREC_FP16X3) SURS_FAIL(ctx, "unknown precision %d", precision);
     return 0;
 }
@@ -295,8 +380,27 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
     if (!ctx) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (check_ready(ctx, precision)) return 1;
     if (plane_lo < 0 || plane_hi > res[0] || plane_lo >= plane_hi) SURS_FAIL(ctx, "surs_eval_grid: bad slab [%d,%d)", plane_lo, plane_hi);
+    // image-coordinate range of the slab (extremes of an affine map over a box are at its corners): a stripe of the
+    // feature maps (surs_set_features_host) is enough when it covers this range
+    float u_lo = -1.0f, u_hi = 1.0f;
+    if (!transform) {
+        double lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {
+            const double step = (b_max[a] - b_min[a]) / res[a];
+            lo[a] = b_min[a] + step * (a == 0 ? plane_lo : 0);
+            hi[a] = b_min[a] + step * ((a == 0 ? plane_hi : res[a]) - 1);
+        }
+        double mn = 1e300, mx = -1e300;
+        for (int c = 0; c < 8; ++c) {
+            const double u = calib[0] * (c & 1 ? hi[0] : lo[0]) + calib[1] * (c & 2 ? hi[1] : lo[1]) + calib[2] * (c & 4 ? hi[2] : lo[2]) + calib[3];
+            mn = u < mn ? u : mn;
+            mx = u > mx ? u : mx;
+        }
+        u_lo = (float)(mn - 1e-5);
+        u_hi = (float)(mx + 1e-5);
+    }
+    if (check_ready(ctx, precision, u_lo, u_hi)) return 1;
     PointIO io;
     memset(&io, 0, sizeof(io));
     if (setup_grid(ctx, io, res, b_min, b_max, transform, st)) return 1;

@@ -40,6 +40,18 @@ def slab_ranges(n_planes, world):
     return out
 
 
+def slab_u_range(res, b_min, b_max, calib, plane_lo, plane_hi):
+    """Range of the image coordinate u = (calib . [x, y, z, 1])[0] (lib/geometry.py:15-31) over the grid nodes of
+    planes [plane_lo, plane_hi): the extremes of an affine map over a box are at its corners."""
+    c = np.asarray(calib, dtype=np.float64).reshape(-1, 4)[0]
+    b_min, b_max = np.asarray(b_min, np.float64), np.asarray(b_max, np.float64)
+    step = (b_max - b_min) / np.asarray(res, np.float64)
+    lo = b_min + step * np.array([plane_lo, 0, 0])
+    hi = b_min + step * (np.array([plane_hi, res[1], res[2]]) - 1)
+    us = [c[0] * (hi[0] if k & 1 else lo[0]) + c[1] * (hi[1] if k & 2 else lo[1]) + c[2] * (hi[2] if k & 4 else lo[2]) + c[3] for k in range(8)]
+    return float(min(us)), float(max(us))
+
+
 def exclusive_offsets(counts):
     """counts [world, k] -> exclusive prefix sums along ranks, [world, k]."""
     c = np.asarray(counts, dtype=np.int64)
@@ -216,8 +228,13 @@ def reconstruction_from_host(ctx, feat_lr_host, feat_hr_host, res, b_min, b_max,
     (lib/mesh_util.py:8-49: verts float64 world coordinates, faces int32, normals, values -- HR then LR) as host
     numpy arrays; the other ranks return None."""
     from .lib.mesh_util import _to_host
-    dev = ctx.device
-    ctx.set_features(feat_lr_host.to(dev, non_blocking=True), feat_hr_host.to(dev, non_blocking=True))
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if distributed else 0
+    world = dist.get_world_size(group) if distributed else 1
+    # this rank only samples the image coordinates u of its slab (+ halo plane): upload that stripe of pixel columns
+    lo, hi = slab_ranges(int(res[0]), world)[rank]
+    hi = min(hi + 1, int(res[0]))
+    ctx.set_features_host(feat_lr_host, feat_hr_host, u_range=slab_u_range(res, b_min, b_max, calib, lo, hi))
     hr, lr = reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, precision=precision, group=group)
     if hr is None:
         return None

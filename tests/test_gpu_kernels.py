@@ -372,6 +372,36 @@ def test_split_operand_mode_dense_and_octree(ctx, case32):
     assert max((a[0] - b[0]).abs().max().item(), (a[1] - b[1]).abs().max().item()) < TOL_X3_MAX
 
 
+def test_feature_stripe_upload_for_slabs(ctx, case32):
+    """surs_set_features_host with a u range uploads only the pixel columns a slab samples: the slab is bit-identical
+    to the one computed from whole maps, and calls that would sample outside the stripe are refused."""
+    from surs_b200 import _capi, parallel
+    res, bmin, bmax = (64, 64, 64), [-0.5] * 3, [0.5] * 3
+    args = (res, bmin, bmax, case32.calib) + znum(case32)
+    full = {p: ctx.eval_grid(*args, precision=p) for p in (_capi.PREC_FP16, _capi.PREC_FP16X3, _capi.PREC_FP32)}
+    f_lr, f_hr = torch.from_numpy(case32.feat_lr).pin_memory(), torch.from_numpy(case32.feat_hr).pin_memory()
+    try:
+        for lo, hi in ((0, 9), (20, 41), (55, 64)):
+            # poison the resident maps, then upload the stripe only
+            ctx.set_features(torch.full_like(f_lr, 7.0).to(ctx.device), torch.full_like(f_hr, -7.0).to(ctx.device))
+            ctx.set_features_host(f_lr, f_hr, u_range=parallel.slab_u_range(res, bmin, bmax, case32.calib, lo, hi))
+            for p, vols in full.items():
+                s_hr, s_lr = ctx.eval_grid(*args, precision=p, plane_lo=lo, plane_hi=hi)
+                assert torch.equal(s_hr, vols[0][lo:hi]) and torch.equal(s_lr, vols[1][lo:hi])
+            if lo > 0:
+                with pytest.raises(RuntimeError, match="stripe"):
+                    ctx.eval_grid(*args, plane_lo=lo - 3, plane_hi=hi)
+            with pytest.raises(RuntimeError, match="stripe"):
+                ctx.query(torch.zeros(3, 4, device=ctx.device), case32.calib, *znum(case32))
+            with pytest.raises(RuntimeError, match="stripe"):
+                ctx.eval_grid_octree(*args, threshold=0.05, init_resolution=16)
+        ctx.set_features_host(f_lr, f_hr)                    # whole maps from the host
+        a = ctx.eval_grid(*args, precision=_capi.PREC_FP16)
+        assert torch.equal(a[0], full[_capi.PREC_FP16][0])
+    finally:
+        load_case(ctx, case32)
+
+
 def test_incremental_layer1_dense_path(ctx, case32, monkeypatch):
     """SURS_COL_INC=1: layer 1 updated incrementally along the column (query_inc.cu) instead of as a
     GEMM -- same occupancies within the fp16 tolerance, deterministic, slabs bit identical."""

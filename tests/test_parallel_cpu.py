@@ -30,6 +30,16 @@ def test_slab_ranges_cover_all_cells_once():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_slab_u_range():
+    calib = np.diag([2.0, -2.0, 2.0, 1.0])
+    lo, hi = parallel.slab_u_range((512, 512, 512), [-0.5] * 3, [0.5] * 3, calib, 64, 129)
+    assert np.isclose(lo, 2 * (-0.5 + 64 / 512)) and np.isclose(hi, 2 * (-0.5 + 128 / 512))
+    sheared = calib.copy()
+    sheared[0, 1] = 0.5                                   # u also depends on y: the range widens by 0.5 * the y extent
+    lo2, hi2 = parallel.slab_u_range((512, 512, 512), [-0.5] * 3, [0.5] * 3, sheared, 64, 129)
+    assert lo2 < lo and hi2 > hi and np.isclose(hi2 - lo2, (hi - lo) + 0.5 * 511 / 512)
+
+
 def test_exclusive_offsets():
     off = parallel.exclusive_offsets([[3, 5], [0, 2], [7, 1]])
     assert off.tolist() == [[0, 0], [3, 5], [3, 7]]
