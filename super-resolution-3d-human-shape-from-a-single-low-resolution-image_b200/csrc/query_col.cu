@@ -1,4 +1,6 @@
-// Column-factored dense grid evaluation (SURS_PREC_FP16, surs_eval_grid without a transform).
+// Column-factored grid evaluation (SURS_PREC_FP16 and SURS_PREC_FP16X3): surs_eval_grid and the levels of
+// surs_eval_grid_octree without a transform; in SURS_PREC_FP16X3 also every other point source, through per-point
+// tables (MODE 2 below).
 //
 // With the calibration used by gen_mesh (lib/train_util.py:63-66: diag(2,-2,2,1)) -- in general
 // whenever calib[0][2] == calib[1][2] == 0 and the grid is not transformed -- the image
@@ -21,7 +23,8 @@
 // 4 564 998 per point.
 //
 // Warp roles (main kernel): 0-7 produce y0 and run the epilogues (warp w: TMEM lanes 32 (w%4)..,
-// column half w/4), 8 = MMA issue, 9 = weight stream + per-column vectors (bulk TMA).
+// column half w/4), 8 = MMA issue (T0 half of layer 1, layers 2 and 3), 9 = weight stream + per-column vectors
+// (bulk TMA), 10 = MMA issue of the T1 half of layer 1 (one-pass mode only).
 #include "col_common.cuh"
 
 #include <new>
@@ -53,7 +56,6 @@ template <int P> struct Ring {
     static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 };
 constexpr int BLOCKS_PER_MLP = 32 + 8 + 4;
-constexpr int KBLK_PER_MLP = 16 + 4 + 4 + 4;             // A-ring K blocks per MLP
 constexpr int NEPI = 8;
 constexpr int NTHREADS = (NEPI + 3) * 32;            // + MMA issue, weight stream, second MMA issue
 
