@@ -166,7 +166,7 @@ def run_ours(args):
     zn, zd = float(case.load_size // 2), float(case.z_size)
     b_min, b_max = np.array([-0.5] * 3), np.array([0.5] * 3)
     mat = bsdf.grid_matrix(res, b_min, b_max)
-    prec = {"fp32": _capi.PREC_FP32, "fp16": _capi.PREC_FP16, "fp16x3": _capi.PREC_FP16X3}[args.precision]
+    prec = {"fp32": _capi.PREC_FP32, "fp16": _capi.PREC_FP16, "fp16x3": _capi.PREC_FP16X3, "fp16r": _capi.PREC_FP16R}[args.precision]
     n_queries = res ** 3
 
     def step():
@@ -222,7 +222,8 @@ def run_ours(args):
     # EXECUTED tensor-core work is 2 x 1 376 256 MAC per point (layers 1-3 only) + the per-column table
     col_flop = 2 * 2 * (512 * 1024 + 256 * 512 + 128 * 256)
     # fp16x3: every product as A_hi.W_hi + A_lo.W_hi + A_hi.W_lo = three times the tensor-core work
-    executed_flop = {_capi.PREC_FP16: col_flop, _capi.PREC_FP16X3: 3 * col_flop}.get(prec, FLOP_PER_QUERY)
+    # (fp16r: the one-pass work; the refinement of a few percent of the nodes is not counted)
+    executed_flop = {_capi.PREC_FP16: col_flop, _capi.PREC_FP16R: col_flop, _capi.PREC_FP16X3: 3 * col_flop}.get(prec, FLOP_PER_QUERY)
     executed = n_slab * executed_flop / (q_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "query_col_kernel (+ col_table_kernel)" if prec != _capi.PREC_FP32 else "query_simt_kernel",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -261,6 +262,21 @@ def run_ours(args):
                     "max_abs_diff_vs_fp32_mode": {"fp16x3": dmax(vx3, v32), "fp16": dmax(v16, v32), "nodes": res * res,
                                                   "note": "pre-threshold occupancy, plane %d of the grid; north_star example tolerance 1e-3" % mid}}
         del v32, v16, vx3
+        # the refined mode (fp16 everywhere + fp16x3 on the nodes the 0.5 iso-surface can depend on): same mesh as fp16x3
+        def step_r():
+            return parallel.reconstruct_slab(ctx, (res, res, res), b_min, b_max, case.calib, zn, zd, mat[:3, :4], precision=_capi.PREC_FP16R)
+        step_r()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(2):
+            step_r()
+        b.record()
+        torch.cuda.synchronize(dev)
+        msr = a.elapsed_time(b) / 2
+        accurate["refined_mode"] = {"precision": "fp16r", "value": n_queries / (msr * 1e-3), "unit": "queries/s", "ms_per_step": msr,
+                                    "refined_fraction": ctx.refined_nodes / float(n_queries),
+                                    "note": "marching-cubes output bit-identical to fp16x3 (tests/test_gpu_fullsize.py)"}
 
     # ---- end to end through the public API with host buffers ------------------------------------
     e2e = None
@@ -349,7 +365,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"fp16": "f16", "fp16x3": "f16x3", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "dtype": {"fp16": "f16", "fp16x3": "f16x3", "fp16r": "f16+f16x3", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": "dense %d^3 reconstruction (query + marching cubes of HR and LR volumes%s), one synthetic %dx%d input, "
                                    "random-init MLP weights" % (res, ", slab-sharded + NCCL mesh gather" if world > 1 else "", args.size, args.size),
                        "resolution": res, "input_side": args.size, "precision": args.precision,
@@ -376,8 +392,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--resolution", type=int, default=512)
     ap.add_argument("--size", type=int, default=512, help="side of the synthetic low-res input image")
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp16x3", "fp32"],
-                    help="fp16: one tensor-core pass (headline); fp16x3: split hi/lo operands, three passes (|d occ| ~2e-5); fp32: CUDA cores")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp16x3", "fp16r", "fp32"],
+                    help="fp16: one tensor-core pass (headline); fp16r: fp16 + fp16x3 on the nodes the iso-surface depends on; fp16x3: split hi/lo operands, three passes (|d occ| ~2e-5); fp32: CUDA cores")
     ap.add_argument("--cpu-points", type=int, default=400000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-x3", action="store_true", help="skip the fp16x3 (split-operand) measurement beside the headline")

@@ -39,12 +39,19 @@ enum {
                            * factored grids (surs_eval_grid / surs_eval_grid_octree without a transform and with
                            * calib[0][2] == calib[1][2] == 0) run at a third of the FP16 rate; every other point
                            * source (surs_query, transformed grids, sheared calibrations) goes through per-point
-                           * tables on the same kernels (~45 M queries/s, 9x the SURS_PREC_FP32 kernel). */
+                           * tables on the same kernels (~45 M queries/s, 9x the SURS_PREC_FP32 kernel). */,
+    SURS_PREC_FP16R = 3   /* "refined": SURS_PREC_FP16 on every node of a dense slab, then SURS_PREC_FP16X3 on the
+                           * nodes the 0.5 iso-surface can depend on (the node or a 6-neighbour within 0.02 of 0.5, or
+                           * an inside / outside change to a neighbour) -- every inside / outside bit and every value
+                           * marching cubes interpolates equals the FP16X3 result, at ~1.2x the FP16 time.  Dense
+                           * column-factored slabs only (surs_eval_grid); elsewhere identical to SURS_PREC_FP16X3. */
 };
 
 #define SURS_NUM_LAYERS 5
 
 int surs_version(void);
+/* nodes re-evaluated with split operands by the last surs_eval_grid(SURS_PREC_FP16R) of this context */
+int64_t surs_refined_nodes(const surs_ctx *ctx);
 
 /* Lifetime.  `device` is a CUDA ordinal. */
 int surs_create(surs_ctx **out, int device);

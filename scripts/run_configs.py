@@ -51,7 +51,7 @@ def main():
     zn, zd = float(case.load_size // 2), float(case.z_size)
     bmin, bmax = np.array([-0.5] * 3), np.array([0.5] * 3)
 
-    prec = {"fp16": _capi.PREC_FP16, "fp16x3": _capi.PREC_FP16X3, "fp32": _capi.PREC_FP32}[os.environ.get("SURS_PRECISION", "fp16")]
+    prec = {"fp16": _capi.PREC_FP16, "fp16x3": _capi.PREC_FP16X3, "fp16r": _capi.PREC_FP16R, "fp32": _capi.PREC_FP32}[os.environ.get("SURS_PRECISION", "fp16")]
 
     def recon(res, octree):
         mat = bsdf.grid_matrix(res, bmin, bmax)[:3, :4]

@@ -18,7 +18,8 @@ LIB_PATH = os.path.join(CSRC, "libsurs.so")
 
 PREC_FP32 = 0
 PREC_FP16 = 1
-PREC_FP16X3 = 2     # split hi/lo fp16 operands on the tensor cores (three MMA passes), column-factored grids
+PREC_FP16X3 = 2     # split hi/lo fp16 operands on the tensor cores (three MMA passes)
+PREC_FP16R = 3      # one pass everywhere + split operands on the nodes the 0.5 iso-surface can depend on (dense grids)
 MC_LOWER_FOREIGN = 1
 
 _P = ctypes.c_void_p
@@ -29,6 +30,7 @@ _lib = None
 # against include/surs.h without a GPU.
 SIGNATURES = {
     "surs_version": (ctypes.c_int, []),
+    "surs_refined_nodes": (_I64, [_P]),
     "surs_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_int]),
     "surs_destroy": (None, [_P]),
     "surs_last_error": (ctypes.c_char_p, [_P]),
@@ -165,6 +167,11 @@ class Context:
             torch.cuda.current_stream(self.device).synchronize()   # inputs are borrowed until the repack ran
 
     # ---- query ----------------------------------------------------------------------
+    @property
+    def refined_nodes(self):
+        """Nodes re-evaluated with split operands by the last eval_grid(precision=PREC_FP16R)."""
+        return int(self.lib.surs_refined_nodes(self._h))
+
     def set_features_host(self, f_lr, f_hr, u_range=None):
         """Feature maps from HOST tensors (NCHW fp32, ideally pinned).  u_range = (u_lo, u_hi): upload only the pixel
         columns that image coordinates in that range sample (slab-parallel ranks); None: the whole maps."""

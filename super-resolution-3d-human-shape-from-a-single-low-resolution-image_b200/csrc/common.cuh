@@ -13,6 +13,8 @@
 #define SURS_C_IMG 320       // gathered image channels (lr then hr, SuRSNet.py:151-153)
 #define SURS_C0_LR 321       // + z_feat
 #define SURS_C0_HR 322       // + masked pred_lr (SuRSNet.py:180)
+#define SURS_REFINE_LEVEL 0.5f   // the iso level of lib/mesh_util.py:40,45
+#define SURS_REFINE_BAND 0.02f   // twice the measured one-pass error bound (max 1.04e-2, profiles/r1_parity_report.json)
 #define SURS_LEAKY 0.01f     // F.leaky_relu default slope (SurfaceClassifier.py:66)
 
 // Where the points of a launch come from (explicit list, dense grid slab, or octree index list)
@@ -34,6 +36,8 @@ struct PointIO {
     // outputs
     float *out_hr, *out_lr;    // fp32, index n (explicit / dense slab)
     double *vol_hr, *vol_lr;   // float64 volumes, index = node (octree scatter); used when non-NULL
+    float *vol32_hr, *vol32_lr; // fp32 slab volumes, index = node - vol32_base (refinement scatter); used when non-NULL
+    int64_t vol32_base;
     int64_t n;
 };
 
@@ -66,6 +70,10 @@ __device__ __forceinline__ void pointio_store(const PointIO &io, int64_t n, floa
         int64_t lin = io.idx_list ? io.idx_list[n] : io.lin_base + n;
         io.vol_hr[lin] = (double)hr;
         io.vol_lr[lin] = (double)lr;
+    } else if (io.vol32_hr) {
+        int64_t lin = (io.idx_list ? io.idx_list[n] : io.lin_base + n) - io.vol32_base;
+        io.vol32_hr[lin] = hr;
+        io.vol32_lr[lin] = lr;
     } else {
         io.out_hr[n] = hr;
         io.out_lr[n] = lr;
@@ -121,6 +129,7 @@ struct surs_ctx {
     int device;
     char err[512];
     int64_t launches;
+    int64_t refined_nodes;                 // SURS_PREC_FP16R: nodes re-evaluated by the last surs_eval_grid
     int sm_count;
     // ---- MLP parameters -------------------------------------------------------
     int have_weights;
@@ -209,5 +218,8 @@ int surs_launch_query_tc(surs_ctx *ctx, const PointIO &io, cudaStream_t st);
 int surs_col_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS], cudaStream_t st);
 int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st, int passes = 1);
 int surs_launch_query_inc(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st);
+// grid.cu
+int surs_refine_select_impl(surs_ctx *ctx, const float *hr, const float *lr, int np, int R1, int R2, int64_t lin_base,
+                            float level, float band, int64_t *idx, int64_t *n_selected, cudaStream_t st);
 // mc.cu
 int surs_mc_init_tables(surs_ctx *ctx);

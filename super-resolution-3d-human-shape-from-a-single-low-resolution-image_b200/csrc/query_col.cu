@@ -80,6 +80,7 @@ struct ColParams {
     int nseg;                      // tiles per column = ceil(R2 / 128)
     int R1, R2, plane_lo;
     int64_t n0, n_end;             // MODE 2: the launch covers points [n0, n_end) of io
+    int64_t col0;                  // MODE 1: the table starts at grid column col0 (a slab's table: plane_lo * R1)
     int ablate;                    // profiling only (SURS_COL_ABLATE): 1 = no weight traffic (results are garbage)
 };
 
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 const int64_t nbase = MODE == 2 ? prm.n0 : 0;
                 n_own = nbase + tile * TILE_M + e.row;
                 node(n_own, col, pr);
+                if (MODE == 1) col -= prm.col0;
                 cv = prm.table + col * CV_ROW_FLOATS;               // this row's column vectors, in global memory
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -373,6 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     Projected q;
                     node(nbase + tile * TILE_M + lane + 32 * r, c, q);
                     zf4[r] = q.zf;
+                    if (MODE == 1) c -= prm.col0;
                     trow4[r] = prm.table + c * CV_ROW_FLOATS;
                 }
             }
@@ -1123,7 +1126,7 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
     prm.nseg = (R2 + TILE_M - 1) / TILE_M;
     prm.ntiles = ncols * prm.nseg;
     prm.R1 = R1; prm.R2 = R2; prm.plane_lo = plane_lo;
-    prm.n0 = 0; prm.n_end = 0;
+    prm.n0 = 0; prm.n_end = 0; prm.col0 = 0;
     prm.ablate = getenv("SURS_COL_ABLATE") ? atoi(getenv("SURS_COL_ABLATE")) : 0;
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
     static const bool profile = getenv("SURS_TC_PROFILE") != nullptr;
@@ -1161,7 +1164,7 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
 // Octree levels through the column table: io is in grid mode with idx_list / vol_* set (n selected nodes of a
 // [R0, R1, R2] grid without transform); the table must cover all R0 x R1 columns (surs_col_build_table with
 // plane_lo = 0), built once per reconstruction.
-int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int R2, cudaStream_t st, int passes)
+int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int R2, cudaStream_t st, int passes, int64_t col0)
 {
     if (io.n <= 0) return 0;
     uint8_t *base = (uint8_t *)ctx->col_weights;
@@ -1172,7 +1175,7 @@ int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int 
     prm.nseg = 1;
     prm.ntiles = (io.n + TILE_M - 1) / TILE_M;
     prm.R1 = R1; prm.R2 = R2; prm.plane_lo = 0;
-    prm.n0 = 0; prm.n_end = 0;
+    prm.n0 = 0; prm.n_end = 0; prm.col0 = col0;
     prm.ablate = 0;
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
     if (passes == 3) {
@@ -1205,7 +1208,7 @@ int surs_launch_query_generic_x3(surs_ctx *ctx, const PointIO &io, cudaStream_t 
         prm.nseg = 1;
         prm.ntiles = (len + TILE_M - 1) / TILE_M;
         prm.R1 = 1; prm.R2 = 1; prm.plane_lo = 0;
-        prm.n0 = s0; prm.n_end = s0 + len;
+        prm.n0 = s0; prm.n_end = s0 + len; prm.col0 = 0;
         prm.ablate = 0;
         const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
         SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<3>::SMEM_TOTAL));

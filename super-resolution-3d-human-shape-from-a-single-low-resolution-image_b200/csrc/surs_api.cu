@@ -82,6 +82,7 @@ extern "C" void surs_destroy(surs_ctx *ctx)
 
 extern "C" const char *surs_last_error(const surs_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
 extern "C" int64_t surs_launch_count(const surs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t surs_refined_nodes(const surs_ctx *ctx) { return ctx ? ctx->refined_nodes : 0; }
 
 // ------------------------------------------------------------------------------------
 // parameters
@@ -284,14 +285,15 @@ static int check_ready(surs_ctx *ctx, int precision, float u_lo = -1.0f, float u
     if (fmaxf(u_lo, -1.0f) < ctx->feat_u_lo - 1e-4f || fminf(u_hi, 1.0f) > ctx->feat_u_hi + 1e-4f)
         SURS_FAIL(ctx, "the resident feature maps cover u in [%g, %g] only (surs_set_features_host stripe); this call samples [%g, %g]",
                   ctx->feat_u_lo, ctx->feat_u_hi, u_lo, u_hi);
-    if (precision != SURS_PREC_FP32 && precision != SURS_PREC_FP16 && precision != SURS_PREC_FP16X3) SURS_FAIL(ctx, "unknown precision %d", precision);
+    if (precision != SURS_PREC_FP32 && precision != SURS_PREC_FP16 && precision != SURS_PREC_FP16X3 && precision != SURS_PREC_FP16R) SURS_FAIL(ctx, "unknown precision %d", precision);
     return 0;
 }
 
 static int run_query(surs_ctx *ctx, const PointIO &io, int precision, cudaStream_t st)
 {
-    // SURS_PREC_FP16X3 without a column structure: per-point tables through the column kernels (query_col.cu)
-    if (precision == SURS_PREC_FP16X3) return surs_launch_query_generic_x3(ctx, io, st);
+    // SURS_PREC_FP16X3 without a column structure: per-point tables through the column kernels (query_col.cu);
+    // SURS_PREC_FP16R only differs from it on dense column-factored slabs (surs_eval_grid)
+    if (precision == SURS_PREC_FP16X3 || precision == SURS_PREC_FP16R) return surs_launch_query_generic_x3(ctx, io, st);
     return precision == SURS_PREC_FP16 ? surs_launch_query_tc(ctx, io, st) : surs_launch_query_simt(ctx, io, st);
 }
 
@@ -418,6 +420,24 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
     const bool col_inc = getenv("SURS_COL_INC") != nullptr;
     if (precision != SURS_PREC_FP32 && !transform && calib[2] == 0.0f && calib[6] == 0.0f && res[2] >= 64 && !no_column) {
         if (precision == SURS_PREC_FP16X3) return surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st, 3);
+        if (precision == SURS_PREC_FP16R) {
+            // one pass everywhere, then split operands on the nodes the 0.5 iso-surface can depend on
+            const int np = plane_hi - plane_lo;
+            if (surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, np, st, 1)) return 1;
+            if (surs_ensure(ctx, (void **)&ctx->idx_list, &ctx->idx_cap, (size_t)io.n * sizeof(int64_t))) return 1;
+            int64_t nsel = 0;
+            if (surs_refine_select_impl(ctx, sdf_hr, sdf_lr, np, res[1], res[2], io.lin_base, SURS_REFINE_LEVEL, SURS_REFINE_BAND,
+                                        ctx->idx_list, &nsel, st)) return 1;
+            ctx->refined_nodes = nsel;
+            if (nsel == 0) return 0;
+            if (surs_col_build_table(ctx, io, res[1], plane_lo, (int64_t)np * res[1], st, 3)) return 1;
+            PointIO part = io;
+            part.idx_list = ctx->idx_list;
+            part.n = nsel;
+            part.out_hr = part.out_lr = nullptr;
+            part.vol32_hr = sdf_hr; part.vol32_lr = sdf_lr; part.vol32_base = io.lin_base;
+            return surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, 3, (int64_t)plane_lo * res[1]);
+        }
         return col_inc ? surs_launch_query_inc(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st)
                        : surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st);
     }
@@ -483,6 +503,7 @@ extern "C" int surs_eval_grid_octree(surs_ctx *ctx, const int res[3], const doub
     io.vol_lr = sdf_lr;
     // Column-table path (same preconditions as the dense column kernels): every W.f product once per column,
     // for all levels; the levels then run the indexed variant of query_col_kernel.  SURS_NO_COLUMN=1 disables it.
+    if (precision == SURS_PREC_FP16R) precision = SURS_PREC_FP16X3;   // the octree already evaluates near the surface only
     const int passes = precision == SURS_PREC_FP16X3 ? 3 : 1;
     const bool use_table = precision != SURS_PREC_FP32 && !transform && calib[2] == 0.0f && calib[6] == 0.0f && getenv("SURS_NO_COLUMN") == nullptr;
     if (use_table && surs_col_build_table(ctx, io, res[1], 0, (int64_t)res[0] * res[1], st, passes)) return 1;

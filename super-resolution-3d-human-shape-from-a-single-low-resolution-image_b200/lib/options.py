@@ -37,7 +37,7 @@ class BaseOptions:
         g.add_argument("--results_path", type=str, default="./results")
         g.add_argument("--load_netG_checkpoint_path", type=str, default=None)
         g.add_argument("--no_octree", action="store_true", help="dense grid instead of the octree (gen_mesh default: octree)")
-        g.add_argument("--precision", type=str, default="fp16", choices=["fp16", "fp16x3", "fp32"],
+        g.add_argument("--precision", type=str, default="fp16", choices=["fp16", "fp16x3", "fp16r", "fp32"],
                        help="fp16: tcgen05 tensor cores, one pass; fp16x3: tensor cores with split hi/lo operands "
                             "(three passes, ~2e-5 from the reference); fp32: CUDA-core exact mode")
         return parser

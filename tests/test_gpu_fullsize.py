@@ -81,6 +81,25 @@ def test_dense_512_split_operand_mode_meets_1e3(big):
         assert ((b - 0.5).abs()[flips] < 1e-4).all()
 
 
+def test_dense_512_refined_mode_gives_the_split_operand_mesh(big):
+    """SURS_PREC_FP16R at the full configuration on a 48-plane slab: the marching-cubes output equals that of the
+    SURS_PREC_FP16X3 slab bit for bit (vertices, faces) while only a few percent of the nodes are re-evaluated."""
+    from surs_b200 import _capi
+    ctx, case, zn, zd, hr, lr = big
+    lo, hi = 232, 280
+    args = ((R, R, R), [-0.5] * 3, [0.5] * 3, case.calib, zn, zd)
+    x3 = ctx.eval_grid(*args, precision=_capi.PREC_FP16X3, plane_lo=lo, plane_hi=hi)
+    ref = ctx.eval_grid(*args, precision=_capi.PREC_FP16R, plane_lo=lo, plane_hi=hi)
+    frac = ctx.refined_nodes / float((hi - lo) * R * R)
+    print("512^3 slab, refined mode: %.2f %% of the nodes re-evaluated" % (100 * frac))
+    assert 0 < frac < 0.25
+    for r, x in zip(ref, x3):
+        assert torch.equal(r > 0.5, x > 0.5)
+        vr, _, fr, _, _, _ = ctx.marching_cubes(r, 0.5)
+        vx, _, fx, _, _, _ = ctx.marching_cubes(x, 0.5)
+        assert torch.equal(fr, fx) and torch.equal(vr, vx)
+
+
 def test_dense_512_slabs_and_repeat_are_bit_identical(big):
     from surs_b200 import _capi
     ctx, case, zn, zd, hr, lr = big

@@ -372,6 +372,48 @@ def test_split_operand_mode_dense_and_octree(ctx, case32):
     assert max((a[0] - b[0]).abs().max().item(), (a[1] - b[1]).abs().max().item()) < TOL_X3_MAX
 
 
+def test_refined_mode_reproduces_the_split_operand_mesh(ctx, case32):
+    """SURS_PREC_FP16R: one pass everywhere + split operands on the nodes the 0.5 iso-surface can depend on.  Every
+    inside / outside bit equals the FP16X3 volume's, every node next to a sign change carries the FP16X3 value, so
+    marching cubes gives the FP16X3 mesh bit for bit; untouched nodes keep the one-pass value."""
+    from surs_b200 import _capi
+    for res, bmax in (((64, 64, 64), [0.5, 0.5, 0.5]), ((40, 50, 128), [0.5, 0.4, 0.55])):
+        args = (res, [-0.5] * 3, bmax, case32.calib) + znum(case32)
+        x3 = ctx.eval_grid(*args, precision=_capi.PREC_FP16X3)
+        one = ctx.eval_grid(*args, precision=_capi.PREC_FP16)
+        ref = ctx.eval_grid(*args, precision=_capi.PREC_FP16R)
+        n_ref = ctx.refined_nodes
+        assert 0 < n_ref < 0.6 * res[0] * res[1] * res[2]
+        changed = 0
+        for r, x, o in zip(ref, x3, one):
+            assert torch.equal(r > 0.5, x > 0.5)
+            same_as_x3, same_as_one = r == x, r == o
+            assert bool((same_as_x3 | same_as_one).all())
+            changed += int((~same_as_one).sum())
+            # nodes with an inside / outside change to a 6-neighbour must carry the split-operand value
+            b = x > 0.5
+            edge = torch.zeros_like(b)
+            for d in range(3):
+                diff = b.narrow(d, 1, b.shape[d] - 1) != b.narrow(d, 0, b.shape[d] - 1)
+                edge.narrow(d, 1, b.shape[d] - 1).logical_or_(diff)
+                edge.narrow(d, 0, b.shape[d] - 1).logical_or_(diff)
+            assert bool(same_as_x3[edge].all())
+            vr, _, fr, _, _, _ = ctx.marching_cubes(r, 0.5)
+            vx, _, fx, _, _, _ = ctx.marching_cubes(x, 0.5)
+            assert torch.equal(fr, fx) and torch.equal(vr, vx)
+        assert changed <= 2 * n_ref
+        print("refined mode %s: %d of %d nodes re-evaluated (%.1f %%)" % (res, n_ref, res[0] * res[1] * res[2], 100.0 * n_ref / (res[0] * res[1] * res[2])))
+    # point sources and the octree: identical to FP16X3
+    p = torch.from_numpy(syn.random_points(700, seed=5)).to(ctx.device)
+    a = ctx.query(p, case32.calib, *znum(case32), precision=_capi.PREC_FP16R)
+    b = ctx.query(p, case32.calib, *znum(case32), precision=_capi.PREC_FP16X3)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    args = ((64, 64, 64), [-0.5] * 3, [0.5] * 3, case32.calib) + znum(case32)
+    oa = ctx.eval_grid_octree(*args, threshold=0.05, init_resolution=16, precision=_capi.PREC_FP16R)
+    ob = ctx.eval_grid_octree(*args, threshold=0.05, init_resolution=16, precision=_capi.PREC_FP16X3)
+    assert torch.equal(oa[0], ob[0]) and torch.equal(oa[1], ob[1]) and oa[2] == ob[2]
+
+
 def test_feature_stripe_upload_for_slabs(ctx, case32):
     """surs_set_features_host with a u range uploads only the pixel columns a slab samples: the slab is bit-identical
     to the one computed from whole maps, and calls that would sample outside the stripe are refused."""
