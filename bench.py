@@ -228,8 +228,8 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "query_col_kernel (+ col_table_kernel)" if prec != _capi.PREC_FP32 else "query_simt_kernel",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one query_col_kernel launch at 512^3, ncu --set full
-                # (profiles/r1_ncu_full_r13_col512.csv): 3.03 GB per-column table read + 1.07 GB volumes written
-                "traffic": 4.096e9 if (world == 1 and res == 512 and prec == _capi.PREC_FP16) else None,
+                # (profiles/r1_ncu_full_final_col512.csv): 3.04 GB per-column table read + 1.06 GB volumes written
+                "traffic": 4.107e9 if (world == 1 and res == 512 and prec == _capi.PREC_FP16) else None,
                 "peak_kind": "%s sustained bf16 (kernel timed inside a 0.3-0.7 s step); burst = %.1f" % (peak_kind, float(peaks["bf16_tflops"])),
                 "kernel_ms": q_ms, "algorithmic_flop_per_query": FLOP_PER_QUERY,
                 "executed_flop_per_query": executed_flop, "executed_tflops": executed, "executed_frac": executed / peak,
