@@ -394,7 +394,7 @@ def main():
     ap.add_argument("--size", type=int, default=512, help="side of the synthetic low-res input image")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp16x3", "fp16r", "fp32"],
                     help="fp16: one tensor-core pass (headline); fp16r: fp16 + fp16x3 on the nodes the iso-surface depends on; fp16x3: split hi/lo operands, three passes (|d occ| ~2e-5); fp32: CUDA cores")
-    ap.add_argument("--cpu-points", type=int, default=400000)
+    ap.add_argument("--cpu-points", type=int, default=800000, help="bounded CPU sample: ~10 s of the torch port on 16 cores")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-x3", action="store_true", help="skip the fp16x3 (split-operand) measurement beside the headline")
     ap.add_argument("--no-cpu", action="store_true")
