@@ -33,7 +33,8 @@ typedef struct surs_ctx surs_ctx;
 /* arithmetic used by the MLP chain */
 enum {
     SURS_PREC_FP32 = 0,   /* CUDA-core fp32 FMA chain; agrees with the reference to ~1e-6     */
-    SURS_PREC_FP16 = 1,   /* tcgen05 tensor cores, fp16 operands / fp32 accumulate (default)   */
+    SURS_PREC_FP16 = 1,   /* tcgen05 tensor cores, fp16 operands / fp32 accumulate, ONE pass: up to 1.5e-2 from the
+                           * reference on sharp weights -- explicit opt-in, not a parity mode                     */
     SURS_PREC_FP16X3 = 2  /* tensor cores with split operands: every product as A_hi.W_hi + A_lo.W_hi + A_hi.W_lo
                            * (fp16 hi/lo pairs, fp32 accumulate), < 1e-4 from the reference's fp32 result.  Column-
                            * factored grids (surs_eval_grid / surs_eval_grid_octree without a transform and with
@@ -41,10 +42,11 @@ enum {
                            * source (surs_query, transformed grids, sheared calibrations) goes through per-point
                            * tables on the same kernels (~45 M queries/s, 9x the SURS_PREC_FP32 kernel). */,
     SURS_PREC_FP16R = 3   /* "refined": SURS_PREC_FP16 on every node of a dense slab, then SURS_PREC_FP16X3 on the
-                           * nodes the 0.5 iso-surface can depend on (the node or a 6-neighbour within 0.02 of 0.5, or
-                           * an inside / outside change to a neighbour) -- every inside / outside bit and every value
-                           * marching cubes interpolates equals the FP16X3 result, at ~1.2x the FP16 time.  Dense
-                           * column-factored slabs only (surs_eval_grid); elsewhere identical to SURS_PREC_FP16X3. */
+                           * nodes the 0.5 iso-surface can depend on (the node or a 6-neighbour within the band of 0.5,
+                           * or an inside / outside change to a neighbour) -- every inside / outside bit and every value
+                           * marching cubes interpolates equals the FP16X3 result, at ~1.2x the FP16 time.  The band is
+                           * verified on every call (surs_refine_stats).  Dense column-factored slabs only
+                           * (surs_eval_grid); elsewhere identical to SURS_PREC_FP16X3.  The host layers' default. */
 };
 
 #define SURS_NUM_LAYERS 5
@@ -52,6 +54,10 @@ enum {
 int surs_version(void);
 /* nodes re-evaluated with split operands by the last surs_eval_grid(SURS_PREC_FP16R) of this context */
 int64_t surs_refined_nodes(const surs_ctx *ctx);
+/* ... and the run-time check of the band: max |one-pass - split| over those nodes, the band, and whether the check
+ * failed (max_diff >= 0.8 band), in which case the whole slab was re-evaluated with SURS_PREC_FP16X3.  Any pointer
+ * may be NULL. */
+int surs_refine_stats(const surs_ctx *ctx, int64_t *nodes, float *max_diff, float *band, int *fell_back);
 
 /* Lifetime.  `device` is a CUDA ordinal. */
 int surs_create(surs_ctx **out, int device);
@@ -176,6 +182,9 @@ int surs_mc_emit_verts(surs_ctx *ctx, const double *mat, float *verts, double *v
                        float *normals, float *values, int64_t vert_id_offset, int plane_offset,
                        int32_t *seam_out, void *stream);
 int surs_mc_emit_faces(surs_ctx *ctx, int32_t *faces, const int32_t *seam_in, void *stream);
+/* Seam edges for which the last surs_mc_emit_faces found seam_in == -1 (the two slabs disagree about an inside /
+ * outside bit of the shared plane; the face then holds -1).  0 on every consistent input.  Synchronises. */
+int64_t surs_mc_seam_violations(surs_ctx *ctx);
 
 /* float64 -> float32 cast of a volume (what skimage does to its input); n elements. */
 int surs_cast_f64_f32(surs_ctx *ctx, const double *src, float *dst, int64_t n, void *stream);

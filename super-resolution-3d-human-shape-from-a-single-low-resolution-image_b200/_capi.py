@@ -16,10 +16,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libsurs.so")
 
-PREC_FP32 = 0
-PREC_FP16 = 1
-PREC_FP16X3 = 2     # split hi/lo fp16 operands on the tensor cores (three MMA passes)
-PREC_FP16R = 3      # one pass everywhere + split operands on the nodes the 0.5 iso-surface can depend on (dense grids)
+PREC_FP32 = 0       # CUDA cores, fp32: the exact mode
+PREC_FP16 = 1       # one tensor-core pass, fp16 operands: explicit opt-in, does NOT meet the 1e-3 tolerance (measured 1.5e-2)
+PREC_FP16X3 = 2     # split hi/lo fp16 operands on the tensor cores (three MMA passes), |d occ| < 1e-4
+PREC_FP16R = 3      # DEFAULT: one pass everywhere + split operands on the nodes the 0.5 iso-surface can depend on
+                    # (dense grids; identical to PREC_FP16X3 on octree / point paths)
+PREC_DEFAULT = PREC_FP16R
 MC_LOWER_FOREIGN = 1
 
 _P = ctypes.c_void_p
@@ -31,6 +33,8 @@ _lib = None
 SIGNATURES = {
     "surs_version": (ctypes.c_int, []),
     "surs_refined_nodes": (_I64, [_P]),
+    "surs_refine_stats": (ctypes.c_int, [_P, _P, _P, _P, _P]),
+    "surs_mc_seam_violations": (_I64, [_P]),
     "surs_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_int]),
     "surs_destroy": (None, [_P]),
     "surs_last_error": (ctypes.c_char_p, [_P]),
@@ -116,6 +120,7 @@ class Context:
             raise RuntimeError(self.lib.surs_last_error(None).decode())
         self._h = h
         self._keep = []
+        self.feature_generation = 0     # bumped by every set_features* call (lib.model.SuRSNet re-uploads when it lags)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -165,12 +170,25 @@ class Context:
             self._check(self.lib.surs_set_features(self._h, _ptr(f_lr), f_lr.shape[0], f_lr.shape[1], f_lr.shape[2],
                                                    _ptr(f_hr), f_hr.shape[0], f_hr.shape[1], f_hr.shape[2], _stream(self.device)))
             torch.cuda.current_stream(self.device).synchronize()   # inputs are borrowed until the repack ran
+        self.feature_generation += 1
 
     # ---- query ----------------------------------------------------------------------
     @property
     def refined_nodes(self):
         """Nodes re-evaluated with split operands by the last eval_grid(precision=PREC_FP16R)."""
         return int(self.lib.surs_refined_nodes(self._h))
+
+    @property
+    def refine_stats(self):
+        """Run-time band check of the last eval_grid(precision=PREC_FP16R): nodes re-evaluated, max |one-pass - split|
+        over them, the band, and whether the check failed (-> the slab was re-evaluated with PREC_FP16X3)."""
+        n, d, b, f = _I64(0), ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int(0)
+        self.lib.surs_refine_stats(self._h, ctypes.byref(n), ctypes.byref(d), ctypes.byref(b), ctypes.byref(f))
+        return {"nodes": int(n.value), "max_diff": float(d.value), "band": float(b.value), "fell_back": bool(f.value)}
+
+    def mc_seam_violations(self):
+        """Seam edges without a vertex id in the last mc_emit_faces (0 unless two slabs disagree on a shared plane)."""
+        return int(self.lib.surs_mc_seam_violations(self._h))
 
     def set_features_host(self, f_lr, f_hr, u_range=None):
         """Feature maps from HOST tensors (NCHW fp32, ideally pinned).  u_range = (u_lo, u_hi): upload only the pixel
@@ -196,8 +214,9 @@ class Context:
                                                         _ptr(f_hr), f_hr.shape[0], f_hr.shape[1], f_hr.shape[2], u_lo, u_hi,
                                                         _stream(self.device)))
             torch.cuda.current_stream(self.device).synchronize()   # the host buffers are borrowed until the copies ran
+        self.feature_generation += 1
 
-    def query(self, points, calib, z_num, z_den, precision=PREC_FP16):
+    def query(self, points, calib, z_num, z_den, precision=PREC_FP16R):
         """points [3,N] fp32 on the device -> (pred_hr, pred_lr) fp32 [N] device tensors."""
         pts = points.detach().to(self.device, torch.float32).contiguous()
         n = pts.shape[1]
@@ -209,7 +228,7 @@ class Context:
                                             _ptr(hr), _ptr(lr), _stream(self.device)))
         return hr, lr
 
-    def query_host(self, points_np, calib, z_num, z_den, precision=PREC_FP16, out_hr=None, out_lr=None):
+    def query_host(self, points_np, calib, z_num, z_den, precision=PREC_FP16R, out_hr=None, out_lr=None):
         """Host in / host out ([3,N] float32 numpy or pinned tensor), copies inside."""
         pts = np.ascontiguousarray(points_np, dtype=np.float32) if not isinstance(points_np, torch.Tensor) else points_np
         n = pts.shape[1]
@@ -233,7 +252,7 @@ class Context:
         tr = None if transform is None else np.ascontiguousarray(np.asarray(transform, dtype=np.float64)[:3, :4])
         return r, bmin, bmax, tr
 
-    def eval_grid(self, res, b_min, b_max, calib, z_num, z_den, transform=None, precision=PREC_FP16,
+    def eval_grid(self, res, b_min, b_max, calib, z_num, z_den, transform=None, precision=PREC_FP16R,
                   plane_lo=0, plane_hi=None):
         """Dense evaluation of planes [plane_lo, plane_hi) -> two fp32 device volumes."""
         plane_hi = res[0] if plane_hi is None else plane_hi
@@ -250,7 +269,7 @@ class Context:
         return hr, lr
 
     def eval_grid_octree(self, res, b_min, b_max, calib, z_num, z_den, threshold, init_resolution=64,
-                         transform=None, precision=PREC_FP16):
+                         transform=None, precision=PREC_FP16R):
         """Octree evaluation -> two float64 device volumes + number of network evaluations."""
         r, bmin, bmax, tr = self._grid_args(res, b_min, b_max, transform)
         shape = tuple(int(v) for v in res)

@@ -14,7 +14,13 @@
 #define SURS_C0_LR 321       // + z_feat
 #define SURS_C0_HR 322       // + masked pred_lr (SuRSNet.py:180)
 #define SURS_REFINE_LEVEL 0.5f   // the iso level of lib/mesh_util.py:40,45
-#define SURS_REFINE_BAND 0.02f   // twice the measured one-pass error bound (max 1.04e-2, profiles/r1_parity_report.json)
+// SURS_PREC_FP16R: nodes within BAND of the level are re-evaluated with split operands.  The band is not trusted, it is
+// VERIFIED on every call: the refinement measures max |one-pass - split| over all re-evaluated nodes (the nodes next to
+// the iso-surface, where the sigmoid is steepest and the one-pass error largest; 10 M samples at 512^3) and, if that
+// exceeds SAFETY x BAND, the whole slab is re-evaluated with split operands (surs_refine_stats reports it).
+// Measured one-pass error on the synthetic saturating weights: max 1.49e-2 (profiles/r1_parity_report.json).
+#define SURS_REFINE_BAND 0.025f
+#define SURS_REFINE_SAFETY 0.8f
 #define SURS_LEAKY 0.01f     // F.leaky_relu default slope (SurfaceClassifier.py:66)
 
 // Where the points of a launch come from (explicit list, dense grid slab, or octree index list)
@@ -38,6 +44,7 @@ struct PointIO {
     double *vol_hr, *vol_lr;   // float64 volumes, index = node (octree scatter); used when non-NULL
     float *vol32_hr, *vol32_lr; // fp32 slab volumes, index = node - vol32_base (refinement scatter); used when non-NULL
     int64_t vol32_base;
+    unsigned *refine_maxdiff;  // refinement scatter: bits of max |old - new| over the overwritten nodes (float >= 0 orders as uint)
     int64_t n;
 };
 
@@ -72,6 +79,10 @@ __device__ __forceinline__ void pointio_store(const PointIO &io, int64_t n, floa
         io.vol_lr[lin] = (double)lr;
     } else if (io.vol32_hr) {
         int64_t lin = (io.idx_list ? io.idx_list[n] : io.lin_base + n) - io.vol32_base;
+        if (io.refine_maxdiff) {
+            const unsigned b = __float_as_uint(fmaxf(fabsf(io.vol32_hr[lin] - hr), fabsf(io.vol32_lr[lin] - lr)));
+            if (b > __ldcg(io.refine_maxdiff)) atomicMax(io.refine_maxdiff, b);   // almost never taken after the first few tiles
+        }
         io.vol32_hr[lin] = hr;
         io.vol32_lr[lin] = lr;
     } else {
@@ -130,6 +141,9 @@ struct surs_ctx {
     char err[512];
     int64_t launches;
     int64_t refined_nodes;                 // SURS_PREC_FP16R: nodes re-evaluated by the last surs_eval_grid
+    float refine_maxdiff;                  // ... max |one-pass - split| over them
+    int refine_fallback;                   // ... 1: the band check failed and the whole slab was re-evaluated with split operands
+    void *mc_faces_stream;                 // stream of the last surs_mc_emit_faces (surs_mc_seam_violations reads its counter)
     int sm_count;
     // ---- MLP parameters -------------------------------------------------------
     int have_weights;

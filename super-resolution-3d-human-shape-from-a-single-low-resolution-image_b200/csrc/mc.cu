@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_verts_kernel(McParams p, i
 // all faces of cell (i,j,k); vbase / fbase = its first vertex / face in this volume's lists
 __device__ __forceinline__ void emit_cell_faces(const McParams &p, int i, int j, int k, const Cell &c, int64_t vbase, int64_t fbase,
                                                 const int32_t *__restrict__ vid, const int32_t *__restrict__ seam_in,
-                                                int64_t id_offset, int32_t *__restrict__ faces)
+                                                int64_t id_offset, int32_t *__restrict__ faces, unsigned long long *seam_bad)
 {
     const uint8_t *rank = p.tb.edge_rank + 13 * c.entry;
     const uint8_t *te = p.tb.tri_edges + 3 * (int)p.tb.tri_off[c.entry];
@@ -345,9 +345,12 @@ __device__ __forceinline__ void emit_cell_faces(const McParams &p, int i, int j,
             if (e == MC_CENTRE) { tri[s] = centre_id; continue; }
             const int axis = c_edge_axis[e];
             const int bi = i + c_edge_base[3 * e], bj = j + c_edge_base[3 * e + 1], bk = k + c_edge_base[3 * e + 2];
-            if (p.lower_foreign && bi == 0 && axis != 0)
+            if (p.lower_foreign && bi == 0 && axis != 0) {
+                // the lower slab owns this vertex; -1 means it saw no sign change on the edge, i.e. the two slabs disagree
+                // about an inside / outside bit of the shared plane: counted, reported by surs_mc_seam_violations
                 tri[s] = seam_in[((int64_t)(axis - 1) * p.R1 + bj) * p.R2 + bk];
-            else
+                if (tri[s] < 0) atomicAdd(seam_bad, 1ull);
+            } else
                 tri[s] = vid[3 * node_lin(p, bi, bj, bk) + axis];
         }
         faces[3 * (fbase + t)] = tri[0];
@@ -358,7 +361,7 @@ __device__ __forceinline__ void emit_cell_faces(const McParams &p, int i, int j,
 
 __global__ void __launch_bounds__(MC_THREADS) mc_emit_faces_kernel(McParams p, int64_t nnode, const uint2 *block_prefix,
                                                                    const int32_t *__restrict__ vid, const int32_t *__restrict__ seam_in,
-                                                                   int64_t id_offset, int32_t *__restrict__ faces)
+                                                                   int64_t id_offset, int32_t *__restrict__ faces, unsigned long long *seam_bad)
 {
     const int64_t lin = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
     Cell c;
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_faces_kernel(McParams p, i
     block_scan2((unsigned)c.nv, (unsigned)c.nt, ea, eb, ta, tb);
     if (c.nt == 0) return;
     const uint2 pre = block_prefix[blockIdx.x];
-    emit_cell_faces(p, i, j, k, c, (int64_t)pre.x + ea, (int64_t)pre.y + eb, vid, seam_in, id_offset, faces);
+    emit_cell_faces(p, i, j, k, c, (int64_t)pre.x + ea, (int64_t)pre.y + eb, vid, seam_in, id_offset, faces, seam_bad);
 }
 
 // ids of the vertices lying in the last plane of axis 0 (for the slab above): [2][R1][R2]
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(128) mc_list_verts_kernel(McParams p, const Ce
 
 __global__ void __launch_bounds__(128) mc_list_faces_kernel(McParams p, const CellRec *__restrict__ cells, const uint4 *__restrict__ boff,
                                                             uint32_t nact, const int32_t *__restrict__ vid, const int32_t *__restrict__ seam_in,
-                                                            int64_t id_offset, int32_t *__restrict__ faces)
+                                                            int64_t id_offset, int32_t *__restrict__ faces, unsigned long long *seam_bad)
 {
     const uint32_t a = blockIdx.x * 128 + threadIdx.x;
     if (a >= nact) return;
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(128) mc_list_faces_kernel(McParams p, const Ce
     cell_coords(p, (int64_t)r.lin, i, j, k);
     Cell c;
     classify(p, i, j, k, c);
-    if (c.nt) emit_cell_faces(p, i, j, k, c, (int64_t)r.vbase, (int64_t)r.fbase, vid, seam_in, id_offset, faces);
+    if (c.nt) emit_cell_faces(p, i, j, k, c, (int64_t)r.vbase, (int64_t)r.fbase, vid, seam_in, id_offset, faces, seam_bad);
 }
 
 struct TableBlob {
@@ -753,18 +756,30 @@ extern "C" int surs_mc_emit_faces(surs_ctx *ctx, int32_t *faces, const int32_t *
     const int64_t nnode = (int64_t)ctx->mc_res[0] * ctx->mc_res[1] * ctx->mc_res[2];
     const int64_t nblocks = (nnode + MC_THREADS - 1) / MC_THREADS;
     McParams p = make_params(ctx);
+    SURS_CUDA(ctx, cudaMemsetAsync(ctx->counter + 8, 0, sizeof(unsigned long long), st));
+    ctx->mc_faces_stream = st;
     if (ctx->mc_nf > 0 && ctx->mc_fast) {
         mc_list_faces_kernel<<<(unsigned)((ctx->mc_nact + 127) / 128), 128, 0, st>>>(p, reinterpret_cast<const CellRec *>(ctx->mc_cells),
                                                                                      reinterpret_cast<const uint4 *>(ctx->mc_cell_tot),
                                                                                      (uint32_t)ctx->mc_nact, ctx->mc_vid, seam_in,
-                                                                                     ctx->mc_id_offset, faces);
+                                                                                     ctx->mc_id_offset, faces, ctx->counter + 8);
         SURS_LAUNCH_CHECK(ctx, "mc_list_faces_kernel");
     } else if (ctx->mc_nf > 0) {
         mc_emit_faces_kernel<<<(unsigned)nblocks, MC_THREADS, 0, st>>>(p, nnode, reinterpret_cast<const uint2 *>(ctx->mc_block_tot), ctx->mc_vid,
-                                                                      seam_in, ctx->mc_id_offset, faces);
+                                                                      seam_in, ctx->mc_id_offset, faces, ctx->counter + 8);
         SURS_LAUNCH_CHECK(ctx, "mc_emit_faces_kernel");
     }
     return 0;
+}
+
+extern "C" int64_t surs_mc_seam_violations(surs_ctx *ctx)
+{
+    if (!ctx) return -1;
+    unsigned long long n = 0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(&n, ctx->counter + 8, sizeof(n), cudaMemcpyDeviceToHost, (cudaStream_t)ctx->mc_faces_stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize((cudaStream_t)ctx->mc_faces_stream) != cudaSuccess) return -1;
+    return (int64_t)n;
 }
 
 extern "C" int surs_mc_emit(surs_ctx *ctx, const double *mat, float *verts, double *verts_world,

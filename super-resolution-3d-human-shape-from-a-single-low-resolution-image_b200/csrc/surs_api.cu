@@ -50,7 +50,7 @@ extern "C" int surs_create(surs_ctx **out, int device)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     cudaSetDevice(device);
-    if (cudaMalloc(&ctx->counter, 64) != cudaSuccess || surs_mc_init_tables(ctx) != 0) {
+    if (cudaMalloc(&ctx->counter, 256) != cudaSuccess || surs_mc_init_tables(ctx) != 0) {
         snprintf(g_create_err, sizeof(g_create_err), "surs_create: device allocation failed: %s", ctx->err);
         delete ctx;
         return 1;
@@ -83,6 +83,15 @@ extern "C" void surs_destroy(surs_ctx *ctx)
 extern "C" const char *surs_last_error(const surs_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
 extern "C" int64_t surs_launch_count(const surs_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int64_t surs_refined_nodes(const surs_ctx *ctx) { return ctx ? ctx->refined_nodes : 0; }
+extern "C" int surs_refine_stats(const surs_ctx *ctx, int64_t *nodes, float *max_diff, float *band, int *fell_back)
+{
+    if (!ctx) return 1;
+    if (nodes) *nodes = ctx->refined_nodes;
+    if (max_diff) *max_diff = ctx->refine_maxdiff;
+    if (band) *band = SURS_REFINE_BAND;
+    if (fell_back) *fell_back = ctx->refine_fallback;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------
 // parameters
@@ -429,14 +438,36 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
             if (surs_refine_select_impl(ctx, sdf_hr, sdf_lr, np, res[1], res[2], io.lin_base, SURS_REFINE_LEVEL, SURS_REFINE_BAND,
                                         ctx->idx_list, &nsel, st)) return 1;
             ctx->refined_nodes = nsel;
+            ctx->refine_maxdiff = 0.0f;
+            ctx->refine_fallback = 0;
             if (nsel == 0) return 0;
             if (surs_col_build_table(ctx, io, res[1], plane_lo, (int64_t)np * res[1], st, 3)) return 1;
+            unsigned *maxdiff = reinterpret_cast<unsigned *>(ctx->counter + 4);
+            SURS_CUDA(ctx, cudaMemsetAsync(maxdiff, 0, sizeof(unsigned), st));
             PointIO part = io;
             part.idx_list = ctx->idx_list;
             part.n = nsel;
             part.out_hr = part.out_lr = nullptr;
             part.vol32_hr = sdf_hr; part.vol32_lr = sdf_lr; part.vol32_base = io.lin_base;
-            return surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, 3, (int64_t)plane_lo * res[1]);
+            part.refine_maxdiff = maxdiff;
+            if (surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, 3, (int64_t)plane_lo * res[1])) return 1;
+            // verify the band on this very input: every re-evaluated node is a sample of the one-pass error
+            unsigned bits = 0;
+            SURS_CUDA(ctx, cudaMemcpyAsync(&bits, maxdiff, sizeof(bits), cudaMemcpyDeviceToHost, st));
+            SURS_CUDA(ctx, cudaStreamSynchronize(st));
+            memcpy(&ctx->refine_maxdiff, &bits, sizeof(float));
+            if (!(ctx->refine_maxdiff < SURS_REFINE_SAFETY * SURS_REFINE_BAND)) {
+                ctx->refine_fallback = 1;
+                static bool warned = false;
+                if (!warned) {
+                    warned = true;
+                    fprintf(stderr, "libsurs: SURS_PREC_FP16R band check failed (max |one-pass - split| = %g >= %g): "
+                                    "re-evaluating the slab with split operands (SURS_PREC_FP16X3)\n",
+                            ctx->refine_maxdiff, SURS_REFINE_SAFETY * SURS_REFINE_BAND);
+                }
+                return surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, np, st, 3);
+            }
+            return 0;
         }
         return col_inc ? surs_launch_query_inc(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st)
                        : surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st);

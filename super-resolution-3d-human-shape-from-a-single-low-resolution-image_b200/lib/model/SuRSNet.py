@@ -35,12 +35,32 @@ _DEFAULT_LR = [321, 1024, 512, 256, 128, 1]
 _DEFAULT_HR = [322, 1024, 512, 256, 128, 1]
 
 
-def _fingerprint(tensors):
-    return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+class _Held:
+    """Identity of a set of tensors that stays sound while we hold it: the tensors themselves are kept (so the
+    caching allocator cannot hand their memory, and CPython cannot hand their id, to a new tensor), together
+    with the version counters in-place operations bump.  ``data_ptr`` catches ``p.data = other``."""
+
+    def __init__(self, tensors):
+        self.tensors = list(tensors)
+        self.marks = [(t._version, t.data_ptr(), tuple(t.shape)) for t in self.tensors]
+
+    def same(self, tensors):
+        tensors = list(tensors)
+        return (len(tensors) == len(self.tensors)
+                and all(a is b for a, b in zip(tensors, self.tensors))
+                and all(m == (t._version, t.data_ptr(), tuple(t.shape)) for m, t in zip(self.marks, tensors)))
+
+
+def _checksum(tensors):
+    """Two norms per tensor, one host read: catches writes that bypass the version counter
+    (``p.data.normal_()``, ``init.normal_(m.weight.data)``).  20 small tensors -> ~0.1 ms."""
+    n2 = torch._foreach_norm(tensors, 2)
+    n1 = torch._foreach_norm(tensors, 1)
+    return tuple(torch.stack(n2 + n1).double().tolist())
 
 
 class SuRSNet(nn.Module):
-    def __init__(self, opt, projection_mode="orthogonal", error_term=None, encoder="auto", precision=_capi.PREC_FP16):
+    def __init__(self, opt, projection_mode="orthogonal", error_term=None, encoder="auto", precision=_capi.PREC_FP16R):
         super().__init__()
         self.name = "surs_b200"
         self.opt = opt
@@ -68,17 +88,61 @@ class SuRSNet(nn.Module):
         else:
             self._builtin = False
         self.encoder = encoder
-        self.im_feat_list_lr = []
-        self.im_feat_list_hr = []
+        self._feat_gen = 0                 # bumped whenever im_feat_list_lr / im_feat_list_hr are (re)assigned
+        self._im_feat_list_lr = []
+        self._im_feat_list_hr = []
         self.intermediate_preds_list_lr = []
         self.intermediate_preds_list_hr = []
         self.im_SR = self.feature_lr = self.feature_hr = None
         self.preds_lr = self.preds_hr = None
         self.labels_lr = self.labels_hr = None
         self._ctx = None
-        self._w_fp = self._f_fp = self._q_fp = None
+        self._w_dirty = True               # MLP parameters must be (re)uploaded
+        self._w_held = self._w_sum = None
+        self._f_held = None                # feature tensors last uploaded (+ the generations they were uploaded at)
+        self._f_gen_uploaded = self._ctx_gen_uploaded = -1
+        self._q_held = None                # (points, calibs) of the last fused query_mr
         self._cached_hr = None
         self._warned = set()
+
+    # ------------------------------------------------------------------ cache invalidation
+    # The library holds packed copies of the MLP weights and repacked copies of the feature maps.  They are
+    # refreshed when: the tensors are different objects / were modified in place (version counter), a cheap
+    # checksum of the 20 MLP tensors changed (writes through ``.data``), ``load_state_dict`` / ``.to()`` /
+    # ``.half()`` ran, ``im_feat_list_*`` were assigned, somebody else replaced the context's features, or the
+    # user calls ``refresh()``.
+    @property
+    def im_feat_list_lr(self):
+        return self._im_feat_list_lr
+
+    @im_feat_list_lr.setter
+    def im_feat_list_lr(self, value):
+        self._im_feat_list_lr = value
+        self._feat_gen += 1
+
+    @property
+    def im_feat_list_hr(self):
+        return self._im_feat_list_hr
+
+    @im_feat_list_hr.setter
+    def im_feat_list_hr(self, value):
+        self._im_feat_list_hr = value
+        self._feat_gen += 1
+
+    def refresh(self):
+        """Forces the next query to re-upload the MLP parameters and the feature maps (needed only after writes
+        the bookkeeping above cannot see, e.g. editing a feature map through ``.data``)."""
+        self._w_dirty = True
+        self._feat_gen += 1
+        self._q_held = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._w_dirty = True
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._w_dirty = True
+        return super().load_state_dict(*args, **kwargs)
 
     # ------------------------------------------------------------------ encoder side (PyTorch)
     def _need_encoder(self):
@@ -122,7 +186,9 @@ class SuRSNet(nn.Module):
             raise RuntimeError("surs_b200 runs on a B200; move the network to a CUDA device (there is no CPU path)")
         if self._ctx is None or self._ctx.device != dev:
             self._ctx = _capi.Context(dev)
-            self._w_fp = self._f_fp = None
+            self._w_dirty = True
+            self._f_held = None
+            self._q_held = None
         return self._ctx
 
     def depth_scale(self):
@@ -148,21 +214,24 @@ class SuRSNet(nn.Module):
         ctx = self.surs_context()
         params = [c.weight for c in self.mlp_lr.layers()] + [c.bias for c in self.mlp_lr.layers()] + \
                  [c.weight for c in self.mlp_hr.layers()] + [c.bias for c in self.mlp_hr.layers()]
-        fp = _fingerprint(params)
-        if fp != self._w_fp:
+        if not self._w_dirty and (self._w_held is None or not self._w_held.same(params)):
+            self._w_dirty = True
+        csum = _checksum(params)
+        if self._w_dirty or csum != self._w_sum:
             ctx.set_weights([c.weight for c in self.mlp_lr.layers()], [c.bias for c in self.mlp_lr.layers()],
                             [c.weight for c in self.mlp_hr.layers()], [c.bias for c in self.mlp_hr.layers()],
                             self.opt.mlp_dim_lr, self.opt.mlp_dim_hr, self.opt.mlp_res_layers_lr)
-            self._w_fp = fp
-            self._q_fp = None
+            self._w_held, self._w_sum, self._w_dirty = _Held(params), csum, False
+            self._q_held = None
         if not self.im_feat_list_lr or not self.im_feat_list_hr:
             raise RuntimeError("image features missing: call filter_lr / filter_hr (or filter) before querying")
         feats = [self.im_feat_list_lr[-1], self.im_feat_list_hr[0]]
-        fp = _fingerprint(feats)
-        if fp != self._f_fp:
+        if (self._f_held is None or self._f_gen_uploaded != self._feat_gen or self._ctx_gen_uploaded != ctx.feature_generation
+                or not self._f_held.same(feats)):
             ctx.set_features(feats[0], feats[1])
-            self._f_fp = fp
-            self._q_fp = None
+            self._f_held = _Held(feats)
+            self._f_gen_uploaded, self._ctx_gen_uploaded = self._feat_gen, ctx.feature_generation
+            self._q_held = None
 
     def _warn_once(self, why):
         if why not in self._warned:
@@ -187,7 +256,7 @@ class SuRSNet(nn.Module):
         self.preds_lr = lr
         self.intermediate_preds_list_lr = [lr]
         self._cached_hr = hr
-        self._q_fp = _fingerprint([points, calibs])
+        self._q_held = _Held([points, calibs]) if torch.is_tensor(calibs) else None
 
     def query_sr(self, points, calibs, transforms=None, labels=None):
         """reference lib/model/SuRSNet.py:161-187 (requires query_mr on the same points first)."""
@@ -195,7 +264,9 @@ class SuRSNet(nn.Module):
             self.labels_hr = labels
         if not self.can_accelerate(calibs, transforms):
             return self._query_sr_torch(points, calibs, transforms)
-        if self._q_fp is not None and self._q_fp == _fingerprint([points, calibs]) and self._cached_hr is not None:
+        # the cached HR result is only valid for the very tensors query_mr saw (object identity while we hold them,
+        # unmodified) and the weights / features it ran with (_sync above clears _q_held when either changed)
+        if self._q_held is not None and self._cached_hr is not None and self._q_held.same([points, calibs]):
             hr = self._cached_hr
         else:
             # different points than query_mr saw: the reference would mix them; we recompute both consistently

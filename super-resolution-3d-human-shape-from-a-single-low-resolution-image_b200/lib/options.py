@@ -37,9 +37,11 @@ class BaseOptions:
         g.add_argument("--results_path", type=str, default="./results")
         g.add_argument("--load_netG_checkpoint_path", type=str, default=None)
         g.add_argument("--no_octree", action="store_true", help="dense grid instead of the octree (gen_mesh default: octree)")
-        g.add_argument("--precision", type=str, default="fp16", choices=["fp16", "fp16x3", "fp16r", "fp32"],
-                       help="fp16: tcgen05 tensor cores, one pass; fp16x3: tensor cores with split hi/lo operands "
-                            "(three passes, ~2e-5 from the reference); fp32: CUDA-core exact mode")
+        g.add_argument("--precision", type=str, default="fp16r", choices=["fp16", "fp16x3", "fp16r", "fp32"],
+                       help="fp16r (default): one tensor-core pass everywhere + split hi/lo operands on every node the 0.5 "
+                            "iso-surface can depend on (mesh identical to fp16x3; octree / point queries run fp16x3); "
+                            "fp16x3: split operands everywhere (three passes, < 1e-4 from the reference); "
+                            "fp32: CUDA-core exact mode; fp16: ONE pass -- explicit opt-in, up to 1.5e-2 from the reference")
         return parser
 
     def parse(self, argv=None):

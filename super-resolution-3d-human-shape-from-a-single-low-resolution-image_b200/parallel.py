@@ -144,7 +144,7 @@ def _mc_contexts(ctx):
     return ctx, sib
 
 
-def reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, transform=None, precision=_capi.PREC_FP16,
+def reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, transform=None, precision=_capi.PREC_FP16R,
                      group=None, gather=True, want_normals=True):
     """Dense reconstruction of this rank's slab + the mesh exchange.  Returns on rank 0 the same
     8-tuple pieces as lib.mesh_util.reconstruction but as device tensors:
@@ -211,6 +211,12 @@ def reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, transform
             items += [(e[2], allc[:, 2 * k]), (e[3], allc[:, 2 * k])]
     got = gather_rows_many(items, 0, group)
     tick("gather of the mesh lists")
+    if rank > 0:
+        # the lower slab owns the vertices of the shared plane; a missing id means the two ranks disagree about an
+        # inside / outside bit there (cannot happen while both evaluate the plane with the same arithmetic)
+        bad = sum(c.mc_seam_violations() for c in ctxs)
+        if bad:
+            raise RuntimeError("slab seam mismatch on rank %d: %d face corners reference a vertex the lower slab does not have" % (rank, bad))
     if rank != 0:
         return (None, None)
     per = 4 if want_normals else 2
@@ -222,7 +228,7 @@ def reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, transform
 
 
 def reconstruction_from_host(ctx, feat_lr_host, feat_hr_host, res, b_min, b_max, calib, z_num, z_den, mat,
-                             precision=_capi.PREC_FP16, group=None):
+                             precision=_capi.PREC_FP16R, group=None):
     """The host-facing multi-GPU call: every rank uploads the two encoder feature maps (NCHW fp32 host tensors,
     ideally pinned) to its GPU, reconstructs its slab, and rank 0 returns the reference's 8-tuple
     (lib/mesh_util.py:8-49: verts float64 world coordinates, faces int32, normals, values -- HR then LR) as host

@@ -78,3 +78,39 @@ def test_product_never_imports_oracle():
                     src = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
                 assert "/root/reference" not in src, fn
+
+
+def test_cache_identity_helpers_are_sound_on_cpu():
+    """lib/model/SuRSNet.py keys its caches on held tensors + version counters + a checksum, never on data_ptr alone."""
+    import torch
+    import importlib
+    M = importlib.import_module("surs_b200.lib.model.SuRSNet")
+    a, b = torch.zeros(4, 3), torch.ones(2)
+    h = M._Held([a, b])
+    assert h.same([a, b])
+    assert not h.same([a.clone(), b]) and not h.same([b, a]) and not h.same([a])
+    a.add_(1.0)                                   # in-place: version counter
+    assert not h.same([a, b])
+    h = M._Held([a, b])
+    a.data = torch.zeros(4, 3)                    # storage swapped under the same object
+    assert not h.same([a, b])
+    w = torch.nn.Parameter(torch.randn(5, 5))
+    c0 = M._checksum([w])
+    v = w._version
+    w.data.normal_()                              # bypasses the version counter (ADVICE r1): the checksum sees it
+    assert w._version == v and M._checksum([w]) != c0
+    # the net's feature lists are properties: assignment bumps a generation, PREC_FP16R is the default
+    from helpers import make_opt
+    net = M.SuRSNet(make_opt(), encoder=None)
+    from surs_b200 import _capi
+    assert net.precision == _capi.PREC_FP16R
+    g = net._feat_gen
+    net.im_feat_list_lr = [torch.zeros(1, 256, 4, 4)]
+    net.im_feat_list_hr = [torch.zeros(1, 64, 8, 8)]
+    assert net._feat_gen == g + 2 and net.im_feat_list_lr[0].shape[1] == 256
+    net._w_dirty = False
+    net.load_state_dict(net.state_dict())
+    assert net._w_dirty
+    net._w_dirty = False
+    net.float()
+    assert net._w_dirty

@@ -37,9 +37,9 @@ class FakeEncoder(torch.nn.Module):
         return [x]
 
 
-def make_net(case, precision=_capi.PREC_FP16, encoder=None):
+def make_net(case, precision=None, encoder=None):
     opt = helpers.make_opt(loadSize=case.load_size, z_size=case.z_size)
-    net = SuRSNet(opt, precision=precision, encoder=encoder).to(DEV).eval()
+    net = (SuRSNet(opt, encoder=encoder) if precision is None else SuRSNet(opt, precision=precision, encoder=encoder)).to(DEV).eval()
     sd = {}
     for name, (ws, bs) in (("mlp_lr", case.mlp_lr), ("mlp_hr", case.mlp_hr)):
         for i, (w, b) in enumerate(zip(ws, bs)):
@@ -83,7 +83,89 @@ def test_query_api_matches_reference_semantics(case32, golden_dir):
     assert np.abs(net.preds_hr[0, 0].detach().cpu().numpy() - g["pred_hr"]).max() < 1e-4
 
 
-@pytest.mark.parametrize("use_octree,res,prec", [(False, 64, _capi.PREC_FP16), (True, 128, _capi.PREC_FP16),
+def test_default_precision_meets_the_tolerance_through_the_public_api(case32, golden_dir):
+    """SuRSNet() without a precision argument = SURS_PREC_FP16R; its query_mr / query_sr / get_preds agree with the
+    reference's golden predictions within THE tolerance (helpers.TOL = 1e-3), flips reported."""
+    g = np.load(os.path.join(golden_dir, "query_golden.npz"))
+    opt, net = make_net(case32)
+    assert net.precision == _capi.PREC_FP16R == _capi.PREC_DEFAULT
+    pts = torch.from_numpy(g["points"])[None].to(DEV)
+    calib = torch.from_numpy(case32.calib)[None].to(DEV)
+    net.query_mr(pts, calib)
+    net.query_sr(pts, calib)
+    hr, lr = net.get_preds()
+    helpers.parity_report(hr[0, 0].cpu(), g["pred_hr"], label="public API, default precision, HR")
+    helpers.parity_report(lr[0, 0].cpu(), g["pred_lr"], label="public API, default precision, LR")
+
+
+def test_cached_state_is_invalidated_soundly(case32):
+    """The library keeps packed weights, repacked features and query_mr's HR result; none of them may go stale:
+    weights edited through .data (no version bump), a new feature tensor that reuses a freed tensor's memory,
+    features replaced behind the net's back, query_sr on other points than query_mr saw."""
+    opt, net = make_net(case32, precision=_capi.PREC_FP32)
+    calib = torch.from_numpy(case32.calib)[None].to(DEV)
+    pts = torch.from_numpy(syn.random_points(3000, seed=3))[None].to(DEV)
+    base = net.query(pts, calib).clone()
+    # 1. in-place write through .data: the version counter does not move, the checksum does
+    w = net.mlp_hr.conv4.weight
+    v0 = w._version
+    w.data.mul_(0.5)
+    assert w._version == v0
+    changed = net.query(pts, calib).clone()
+    assert not torch.equal(changed, base)
+    w.data.mul_(2.0)
+    assert torch.equal(net.query(pts, calib), base)
+    # 2. load_state_dict / .to() mark the weights dirty
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    sd["mlp_lr.conv0.bias"] += 0.25
+    net.load_state_dict(sd)
+    assert not torch.equal(net.query(pts, calib), base)
+    sd["mlp_lr.conv0.bias"] -= 0.25
+    net.load_state_dict(sd)
+    assert torch.allclose(net.query(pts, calib), base, atol=1e-6)
+    base = net.query(pts, calib).clone()
+    # 3. a new feature tensor in recycled memory (same data_ptr / version / shape as the freed one)
+    other = syn.SyntheticCase(S=32, seed=5)
+    net.im_feat_list_lr, net.im_feat_list_hr = [], []
+    ptrs = set()
+    f_lr = torch.from_numpy(case32.feat_lr)[None].to(DEV); f_hr = torch.from_numpy(case32.feat_hr)[None].to(DEV)
+    net.im_feat_list_lr, net.im_feat_list_hr = [f_lr], [f_hr]
+    a = net.query(pts, calib).clone()
+    ptrs.add(f_lr.data_ptr())
+    del f_lr, f_hr
+    net.im_feat_list_lr, net.im_feat_list_hr = [], []
+    g_lr = torch.from_numpy(other.feat_lr)[None].to(DEV); g_hr = torch.from_numpy(other.feat_hr)[None].to(DEV)
+    net.im_feat_list_lr, net.im_feat_list_hr = [g_lr], [g_hr]
+    b = net.query(pts, calib).clone()
+    print("recycled feature memory:", g_lr.data_ptr() in ptrs)
+    assert not torch.equal(a, b)
+    # 4. somebody replaces the context's features behind the net's back
+    ctx = net.surs_context()
+    ctx.set_features(torch.from_numpy(case32.feat_lr).to(DEV), torch.from_numpy(case32.feat_hr).to(DEV))
+    assert torch.equal(net.query(pts, calib), b)                       # the net re-uploads ITS features
+    # 5. query_sr on other points than query_mr: recomputed, never the cached HR of the other points
+    pts2 = torch.from_numpy(syn.random_points(3000, seed=4))[None].to(DEV)
+    want2 = net.query(pts2, calib).clone()
+    net.query_mr(pts, calib)
+    net.query_sr(pts2, calib)
+    assert torch.equal(net.get_preds()[0], want2)
+    # ... also when the second tensor reuses the first one's memory
+    net.query_mr(pts, calib)
+    p_tmp = pts.clone()
+    net.query_mr(p_tmp, calib)
+    del p_tmp
+    p_new = pts2.clone()
+    net.query_sr(p_new, calib)
+    assert torch.equal(net.get_preds()[0], want2)
+    # 6. in-place edit of the points between query_mr and query_sr
+    p3 = pts.clone()
+    net.query_mr(p3, calib)
+    p3.copy_(pts2)
+    net.query_sr(p3, calib)
+    assert torch.equal(net.get_preds()[0], want2)
+
+
+@pytest.mark.parametrize("use_octree,res,prec", [(False, 64, _capi.PREC_FP16R), (True, 128, _capi.PREC_FP16R), (False, 64, _capi.PREC_FP16),
                                                  (False, 64, _capi.PREC_FP16X3), (True, 128, _capi.PREC_FP16X3)])
 def test_reconstruction_fast_path(case32, use_octree, res, prec):
     opt, net = make_net(case32, precision=prec)
