@@ -133,6 +133,13 @@ int surs_eval_grid_octree(surs_ctx *ctx, const int res[3], const double b_min[3]
                           int precision, int init_resolution, double threshold,
                           double *sdf_hr, double *sdf_lr, int64_t *n_evaluated, void *stream);
 
+/* Phase statistics of the last surs_eval_grid_octree on this context (synchronises on its events):
+ *   ms[5]     = device time of {volume / dirty initialisation, per-column table, select, network evaluation, cell pass}
+ *   counts[6] = {lattice candidates read by select, nodes evaluated, cells visited by the cell pass,
+ *                cells whose 16 corners were read, nodes block-filled in HR, nodes block-filled in LR}
+ * -- the terms of the octree bookkeeping's HBM roofline (bench.py's `roofline_octree`). */
+int surs_octree_stats(surs_ctx *ctx, float ms[5], int64_t counts[6]);
+
 /* Building blocks of the octree for callers that bring their own eval_func (the generic
  * lib/sdf.py path): `surs_octree_select` marks grid_mask & dirty nodes of level `reso`
  * (lib/sdf.py:70-74) and writes their linear indices (C-order) to idx [dev, capacity

@@ -18,11 +18,33 @@ import sys
 import types
 import argparse
 
-REF_ROOT = os.environ.get("SURS_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_MOUNT = os.environ.get("SURS_REFERENCE_ROOT", "/root/reference")
+# the read-only mount when it exists (build container), else the verbatim copy oracle/make_ref.py made of it
+# (oracle/_ref: git-ignored, travels to the GPU box with gpurun; only bench.py's CPU legs use it there)
+REF_ROOT = _MOUNT if os.path.isdir(os.path.join(_MOUNT, "lib")) else os.path.join(_HERE, "_ref" if not os.environ.get("SURS_NO_REF_COPY") else "_none")
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "lib"))
+
+
+def is_mount() -> bool:
+    return REF_ROOT == _MOUNT
+
+
+def use_marching_cubes(fn):
+    """Routes the reference's ``measure.marching_cubes_lewiner`` (lib/mesh_util.py:40,45) to ``fn`` -- the oracle's C
+    twin when scikit-image is absent (labelled as such wherever a number is reported)."""
+    _stub_skimage()
+    sys.modules["skimage.measure"].marching_cubes_lewiner = fn
+    if "lib.mesh_util" in sys.modules:
+        sys.modules["lib.mesh_util"].measure.marching_cubes_lewiner = fn
+
+
+def have_real_skimage() -> bool:
+    m = sys.modules.get("skimage")
+    return m is not None and getattr(m, "__file__", None) is not None
 
 
 def _stub_skimage():

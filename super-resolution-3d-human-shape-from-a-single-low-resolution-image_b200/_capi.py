@@ -49,6 +49,7 @@ SIGNATURES = {
                                       ctypes.c_int, ctypes.c_int, _P, _P, _P]),
     "surs_eval_grid_octree": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_int,
                                              ctypes.c_int, ctypes.c_double, _P, _P, _P, _P]),
+    "surs_octree_stats": (ctypes.c_int, [_P, _P, _P]),
     "surs_octree_select": (ctypes.c_int, [_P, _P, ctypes.c_int, _P, _P, _P, _P]),
     "surs_octree_cells": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_double, _P, _P, _P, _P]),
     "surs_mc_count": (ctypes.c_int, [_P, _P, _P, ctypes.c_float, ctypes.c_int, _P, _P, _P, _P]),
@@ -284,6 +285,15 @@ class Context:
                                                        float(threshold), _ptr(hr), _ptr(lr), ctypes.byref(n_eval),
                                                        _stream(self.device)))
         return hr, lr, int(n_eval.value)
+
+    def octree_stats(self):
+        """Phase times (ms) and counts of the last eval_grid_octree (include/surs.h: surs_octree_stats)."""
+        ms = (ctypes.c_float * 5)()
+        cnt = (_I64 * 6)()
+        self._check(self.lib.surs_octree_stats(self._h, ms, cnt))
+        out = dict(zip(("init_ms", "table_ms", "select_ms", "query_ms", "cells_ms"), [float(v) for v in ms]))
+        out.update(zip(("candidates", "evaluated", "cells", "cells_read", "filled_hr", "filled_lr"), [int(v) for v in cnt]))
+        return out
 
     def octree_select(self, res, reso, dirty, idx):
         r = (ctypes.c_int * 3)(*[int(v) for v in res])

@@ -176,7 +176,14 @@ struct surs_ctx {
     size_t dirty_cap;
     int64_t *idx_list;                     // octree compaction output
     size_t idx_cap;
-    unsigned long long *counter;           // device scalar(s)
+    unsigned long long *counter;           // device scalars: [0..7] select / marching cubes, [4] refinement max diff, [8] seam
+                                           // violations, [16..18] octree statistics
+    // phase timing of the last surs_eval_grid_octree (surs_octree_stats): event pairs, phase id per pair
+    void *oct_ev[64];
+    int oct_phase[32];
+    int oct_npairs;
+    int64_t oct_candidates, oct_evaluated, oct_cells;
+    int oct_res[3];
     float *stage_pts, *stage_out;          // staging for surs_query_host
     size_t stage_cap;
     // ---- marching cubes state (between count and emit) ---------------------------

@@ -137,10 +137,20 @@ __device__ __forceinline__ Range corner_range(const double *__restrict__ v, int6
 }
 
 // pass A: one thread per cell (origins in range(0, R - reso, reso), lib/sdf.py:81-83)
+// stats[0] += cells whose 16 corners were read, stats[1] / stats[2] += nodes the fill pass will write in HR / LR
 __global__ void octree_decide_kernel(double *__restrict__ hr, double *__restrict__ lr, uint8_t *__restrict__ dirty,
-                                     int R1, int R2, int m1, int m2, int64_t ncell, int reso, double threshold)
+                                     int R1, int R2, int m1, int m2, int64_t ncell, int reso, double threshold,
+                                     unsigned long long *stats)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c < ncell && [&] {
+        const int cz = (int)(c % m2);
+        const int64_t t = c / m2;
+        const int64_t o = ((int64_t)(t / m1) * reso * R1 + (int64_t)(t % m1) * reso) * R2 + (int64_t)cz * reso;
+        return dirty[o + (int64_t)(reso / 2) * ((int64_t)R1 * R2 + R2 + 1)] == 1;
+    }();
+    const int nlive = __syncthreads_count(live);
+    if (threadIdx.x == 0 && nlive) atomicAdd(stats, (unsigned long long)nlive);
     if (c >= ncell) return;
     const int cz = (int)(c % m2);
     const int64_t t = c / m2;
@@ -156,6 +166,9 @@ __global__ void octree_decide_kernel(double *__restrict__ hr, double *__restrict
     if (__dsub_rn(a.hi, a.lo) < threshold) { hr[centre] = __dadd_rn(a.hi, a.lo) / 2.0; code |= 2; }   // :97-101
     if (__dsub_rn(b.hi, b.lo) < threshold) { lr[centre] = __dadd_rn(b.hi, b.lo) / 2.0; code |= 4; }   // :113-117
     if (code) dirty[centre] = (uint8_t)code;
+    const unsigned long long vox = (unsigned long long)reso * reso * reso - 1;
+    if (code & 2) atomicAdd(stats + 1, vox);
+    if (code & 4) atomicAdd(stats + 2, vox);
 }
 
 // pass B: one thread per node, coalesced along the last axis
@@ -223,7 +236,7 @@ int surs_octree_cells_impl(surs_ctx *ctx, const int res[3], int reso, double thr
     const int64_t ncell = (int64_t)m[0] * m[1] * m[2];
     if (ncell == 0) return 0;
     octree_decide_kernel<<<(unsigned)((ncell + 127) / 128), 128, 0, st>>>(sdf_hr, sdf_lr, dirty, res[1], res[2],
-                                                                         m[1], m[2], ncell, reso, threshold);
+                                                                         m[1], m[2], ncell, reso, threshold, ctx->counter + 16);
     SURS_LAUNCH_CHECK(ctx, "octree_decide_kernel");
     if (res[1] > 65535 || res[0] > 65535) SURS_FAIL(ctx, "octree: resolution too large");
     dim3 grid((res[2] + 127) / 128, res[1], res[0]);

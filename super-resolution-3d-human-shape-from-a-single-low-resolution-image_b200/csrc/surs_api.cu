@@ -76,6 +76,8 @@ extern "C" void surs_destroy(surs_ctx *ctx)
     cudaFree(ctx->f_lr32); cudaFree(ctx->f_hr32); cudaFree(ctx->f_lr16); cudaFree(ctx->f_hr16); cudaFree(ctx->feat_stage);
     cudaFree(ctx->axis_dev); cudaFree(ctx->dirty); cudaFree(ctx->idx_list); cudaFree(ctx->counter);
     cudaFree(ctx->stage_pts); cudaFree(ctx->stage_out);
+    for (int k = 0; k < 64; ++k)
+        if (ctx->oct_ev[k]) cudaEventDestroy((cudaEvent_t)ctx->oct_ev[k]);
     cudaFree(ctx->mc_block_tot); cudaFree(ctx->mc_bits); cudaFree(ctx->mc_cell_tot); cudaFree(ctx->mc_cells); cudaFree(ctx->mc_vid); cudaFree(ctx->mc_tables);
     delete ctx;
 }
@@ -507,6 +509,47 @@ extern "C" int surs_octree_cells(surs_ctx *ctx, const int res[3], int reso, doub
     return surs_octree_cells_impl(ctx, res, reso, threshold, sdf_hr, sdf_lr, dirty, (cudaStream_t)stream);
 }
 
+// phase timing of the octree: CUDA event pairs on the call's stream, summed by surs_octree_stats
+namespace {
+enum { OCT_INIT = 0, OCT_TABLE = 1, OCT_SELECT = 2, OCT_QUERY = 3, OCT_CELLS = 4, OCT_NPHASE = 5 };
+struct OctPhase {
+    surs_ctx *ctx;
+    cudaStream_t st;
+    int pair;
+    OctPhase(surs_ctx *c, cudaStream_t s, int phase) : ctx(c), st(s), pair(-1)
+    {
+        if (ctx->oct_npairs >= 32) return;
+        pair = ctx->oct_npairs++;
+        for (int k = 0; k < 2; ++k)
+            if (!ctx->oct_ev[2 * pair + k]) cudaEventCreate((cudaEvent_t *)&ctx->oct_ev[2 * pair + k]);
+        ctx->oct_phase[pair] = phase;
+        cudaEventRecord((cudaEvent_t)ctx->oct_ev[2 * pair], st);
+    }
+    ~OctPhase() { if (pair >= 0) cudaEventRecord((cudaEvent_t)ctx->oct_ev[2 * pair + 1], st); }
+};
+}  // namespace
+
+extern "C" int surs_octree_stats(surs_ctx *ctx, float ms[5], int64_t counts[6])
+{
+    if (!ctx) return 1;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    float acc[OCT_NPHASE] = {0, 0, 0, 0, 0};
+    for (int p = 0; p < ctx->oct_npairs; ++p) {
+        SURS_CUDA(ctx, cudaEventSynchronize((cudaEvent_t)ctx->oct_ev[2 * p + 1]));
+        float t = 0.0f;
+        SURS_CUDA(ctx, cudaEventElapsedTime(&t, (cudaEvent_t)ctx->oct_ev[2 * p], (cudaEvent_t)ctx->oct_ev[2 * p + 1]));
+        acc[ctx->oct_phase[p]] += t;
+    }
+    if (ms) memcpy(ms, acc, sizeof(acc));
+    if (counts) {
+        unsigned long long dev[3] = {0, 0, 0};
+        SURS_CUDA(ctx, cudaMemcpy(dev, ctx->counter + 16, sizeof(dev), cudaMemcpyDeviceToHost));
+        counts[0] = ctx->oct_candidates; counts[1] = ctx->oct_evaluated; counts[2] = ctx->oct_cells;
+        counts[3] = (int64_t)dev[0]; counts[4] = (int64_t)dev[1]; counts[5] = (int64_t)dev[2];
+    }
+    return 0;
+}
+
 extern "C" int surs_eval_grid_octree(surs_ctx *ctx, const int res[3], const double b_min[3], const double b_max[3],
                                      const double *transform, const float calib[12], float z_num, float z_den,
                                      int precision, int init_resolution, double threshold,
@@ -518,14 +561,21 @@ extern "C" int surs_eval_grid_octree(surs_ctx *ctx, const int res[3], const doub
     if (check_ready(ctx, precision)) return 1;
     if (init_resolution < 1) SURS_FAIL(ctx, "surs_eval_grid_octree: bad init_resolution");
     const size_t nnode = (size_t)res[0] * res[1] * res[2];
-    // lib/sdf.py:60-64: zeros, dirty = ones
-    SURS_CUDA(ctx, cudaMemsetAsync(sdf_hr, 0, nnode * sizeof(double), st));
-    SURS_CUDA(ctx, cudaMemsetAsync(sdf_lr, 0, nnode * sizeof(double), st));
+    ctx->oct_npairs = 0;
+    ctx->oct_candidates = ctx->oct_evaluated = ctx->oct_cells = 0;
+    memcpy(ctx->oct_res, res, sizeof(int) * 3);
     if (n_evaluated) *n_evaluated = 0;
     int reso = res[0] / init_resolution;                        // lib/sdf.py:66
-    if (reso <= 0) return 0;                                    // the reference returns zeros
-    if (surs_ensure(ctx, (void **)&ctx->dirty, &ctx->dirty_cap, nnode)) return 1;
-    SURS_CUDA(ctx, cudaMemsetAsync(ctx->dirty, 1, nnode, st));
+    {
+        OctPhase ph(ctx, st, OCT_INIT);
+        // lib/sdf.py:60-64: zeros, dirty = ones
+        SURS_CUDA(ctx, cudaMemsetAsync(sdf_hr, 0, nnode * sizeof(double), st));
+        SURS_CUDA(ctx, cudaMemsetAsync(sdf_lr, 0, nnode * sizeof(double), st));
+        SURS_CUDA(ctx, cudaMemsetAsync(ctx->counter + 16, 0, 3 * sizeof(unsigned long long), st));
+        if (reso <= 0) return 0;                                // the reference returns zeros
+        if (surs_ensure(ctx, (void **)&ctx->dirty, &ctx->dirty_cap, nnode)) return 1;
+        SURS_CUDA(ctx, cudaMemsetAsync(ctx->dirty, 1, nnode, st));
+    }
     PointIO io;
     memset(&io, 0, sizeof(io));
     if (setup_grid(ctx, io, res, b_min, b_max, transform, st)) return 1;
@@ -537,22 +587,39 @@ extern "C" int surs_eval_grid_octree(surs_ctx *ctx, const int res[3], const doub
     if (precision == SURS_PREC_FP16R) precision = SURS_PREC_FP16X3;   // the octree already evaluates near the surface only
     const int passes = precision == SURS_PREC_FP16X3 ? 3 : 1;
     const bool use_table = precision != SURS_PREC_FP32 && !transform && calib[2] == 0.0f && calib[6] == 0.0f && getenv("SURS_NO_COLUMN") == nullptr;
-    if (use_table && surs_col_build_table(ctx, io, res[1], 0, (int64_t)res[0] * res[1], st, passes)) return 1;
+    if (use_table) {
+        OctPhase ph(ctx, st, OCT_TABLE);
+        if (surs_col_build_table(ctx, io, res[1], 0, (int64_t)res[0] * res[1], st, passes)) return 1;
+    }
     while (reso > 0) {
         const size_t cand = (size_t)((res[0] + reso - 1) / reso) * ((res[1] + reso - 1) / reso) * ((res[2] + reso - 1) / reso);
         if (surs_ensure(ctx, (void **)&ctx->idx_list, &ctx->idx_cap, cand * sizeof(int64_t))) return 1;
         int64_t nsel = 0;
-        if (surs_octree_select_impl(ctx, res, reso, ctx->dirty, ctx->idx_list, &nsel, st)) return 1;
+        {
+            OctPhase ph(ctx, st, OCT_SELECT);
+            if (surs_octree_select_impl(ctx, res, reso, ctx->dirty, ctx->idx_list, &nsel, st)) return 1;
+        }
+        ctx->oct_candidates += (int64_t)cand;
+        ctx->oct_evaluated += nsel;
         if (n_evaluated) *n_evaluated += nsel;
         const int64_t chunk = (int64_t)1 << 30;
-        for (int64_t s = 0; s < nsel; s += chunk) {
-            PointIO part = io;
-            part.idx_list = ctx->idx_list + s;
-            part.n = (nsel - s < chunk) ? nsel - s : chunk;
-            if (use_table ? surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, passes) : run_query(ctx, part, precision, st)) return 1;
+        {
+            OctPhase ph(ctx, st, OCT_QUERY);
+            for (int64_t s = 0; s < nsel; s += chunk) {
+                PointIO part = io;
+                part.idx_list = ctx->idx_list + s;
+                part.n = (nsel - s < chunk) ? nsel - s : chunk;
+                if (use_table ? surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, passes) : run_query(ctx, part, precision, st)) return 1;
+            }
         }
         if (reso <= 1) break;                                   // lib/sdf.py:79
-        if (surs_octree_cells_impl(ctx, res, reso, threshold, sdf_hr, sdf_lr, ctx->dirty, st)) return 1;
+        {
+            OctPhase ph(ctx, st, OCT_CELLS);
+            if (surs_octree_cells_impl(ctx, res, reso, threshold, sdf_hr, sdf_lr, ctx->dirty, st)) return 1;
+        }
+        int64_t ncell = 1;
+        for (int a = 0; a < 3; ++a) ncell *= res[a] > reso ? (res[a] - 1) / reso : 0;
+        ctx->oct_cells += ncell;
         reso /= 2;
     }
     return 0;
