@@ -179,10 +179,14 @@ int surs_octree_cells(surs_ctx *ctx, const int res[3], int reso, double threshol
  * So: count everywhere -> exchange counts -> emit_verts everywhere -> pass seam_out up ->
  * emit_faces everywhere -> concatenate in rank order.
  * n_ambiguous [host, may be NULL]: number of cells with an ambiguous face (the part of the
- * Lewiner algorithm whose parity with scikit-image is unpinned). */
+ * Lewiner algorithm whose parity with scikit-image is unpinned).
+ * surs_mc_interior_stats: cells of the last surs_mc_count whose face decisions left an INTERIOR ambiguity (two
+ * same-sign regions that the trilinear interpolant may join by a tunnel: Lewiner's cases 4, 6, 7, 10, 12, 13) and
+ * how many of them took the tunnel triangulation (csrc/gen_mc_tables.py).  Synchronises. */
 enum { SURS_MC_LOWER_FOREIGN = 1 };
 int surs_mc_count(surs_ctx *ctx, const float *vol, const int res[3], float level, int flags,
                   int64_t *n_verts, int64_t *n_faces, int64_t *n_ambiguous, void *stream);
+int surs_mc_interior_stats(surs_ctx *ctx, int64_t *n_interior_ambiguous, int64_t *n_tunnels);
 int surs_mc_emit(surs_ctx *ctx, const double *mat, float *verts, double *verts_world,
                  int32_t *faces, float *normals, float *values, void *stream);
 int surs_mc_emit_verts(surs_ctx *ctx, const double *mat, float *verts, double *verts_world,

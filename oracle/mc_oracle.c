@@ -20,9 +20,11 @@
  *     evaluated in double, stored float32, reported in (axis0, axis1, axis2) order;
  *   - degenerate triangles kept.
  *
- * Deviations (documented in oracle/gen_mc_tables.py): derived case tables (no interior
- * test; own loop triangulation; the centre vertex is used where a loop cannot be
- * triangulated without a diagonal lying in a cube face).  `normals` / `values` are
+ * Deviations (documented in csrc/gen_mc_tables.py): derived case tables (own loop / band
+ * triangulation; the centre vertex is used where a loop cannot be triangulated without a
+ * diagonal lying in a cube face; the interior (tunnel) test is derived from the trilinear
+ * sections rather than Lewiner's per-case reference edges).  The tables are shared with the
+ * kernels (mc_tables.h): what checks THEM is the table-free oracle/mc_check.py.  `normals` / `values` are
  * API-shape obligations only (the reference's caller discards them, lib/train_util.py:72):
  * normals = normalised volume gradient (central differences, linear along the edge),
  * values = max of the edge's two end values.
@@ -43,6 +45,28 @@
 
 #define IDX(i, j, k) (((int64_t)(i) * R1 + (j)) * R2 + (k))
 
+/* Interior (tunnel) test: csrc/gen_mc_tables.py; same operation order as csrc/mc.cu interior_test. */
+static int interior_test(const double d[8], const uint8_t *cn, int s)
+{
+    double a0 = d[cn[0]], a1 = d[cn[1]], b0 = d[cn[2]], b1 = d[cn[3]], c0 = d[cn[4]], c1 = d[cn[5]], d0 = d[cn[6]], d1 = d[cn[7]];
+    double dA = a1 - a0, dB = b1 - b0, dC = c1 - c0, dD = d1 - d0;
+    double qa = dA * dC - dB * dD;
+    double qb = (a0 * dC + c0 * dA) - (b0 * dD + d0 * dB);
+    if (!(qa < 0.0)) return 0;
+    double t = -qb / (2.0 * qa);
+    if (!(t > 0.0 && t < 1.0)) return 0;
+    double At = a0 + dA * t, Bt = b0 + dB * t, Ct = c0 + dC * t, Dt = d0 + dD * t;
+    if (s) {
+        if (!(At > 0.0 && Ct > 0.0)) return 0;
+    } else if (At > 0.0 || Ct > 0.0) {
+        return 0;
+    }
+    return At * Ct - Bt * Dt > 0.0;
+}
+
+static int64_t g_interior = 0, g_tunnels = 0;      /* statistics of the last run (single-threaded test code) */
+void mc_oracle_interior_stats(int64_t *n_interior, int64_t *n_tunnels) { *n_interior = g_interior; *n_tunnels = g_tunnels; }
+
 static int cell_entry(const float *vol, int R1, int R2, int i, int j, int k, double level, double d[8])
 {
     int c, f, cas = 0;
@@ -60,7 +84,18 @@ static int cell_entry(const float *vol, int R1, int R2, int i, int j, int k, dou
         var |= connect << nb;
         ++nb;
     }
-    return mc_var_base[cas] + var;
+    int ent = mc_var_base[cas] + var;
+    if (mc_ntest[ent]) {
+        ++g_interior;
+        for (int q = 0; q < mc_ntest[ent]; ++q) {
+            int tq = mc_test_off[ent] + q;
+            if (interior_test(d, &mc_test_corners[8 * tq], mc_test_sign[tq])) {
+                ++g_tunnels;
+                return mc_test_target[tq];
+            }
+        }
+    }
+    return ent;
 }
 
 static double node_grad(const float *vol, int R0, int R1, int R2, int i, int j, int k, int axis)
@@ -119,6 +154,7 @@ int mc_oracle_run(const float *vol, int R0, int R1, int R2, float level_f,
 {
     const double level = (double)level_f;
     int64_t nnode = (int64_t)R0 * R1 * R2, nv = 0, nf = 0, namb = 0;
+    g_interior = g_tunnels = 0;
     int32_t *vid = (int32_t *)malloc(sizeof(int32_t) * 3 * (size_t)nnode);
     if (!vid) return -1;
     memset(vid, 0xff, sizeof(int32_t) * 3 * (size_t)nnode);

@@ -31,6 +31,8 @@ def _lib():
         lib.mc_oracle_run.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                       P, P, P, P, P, P, P]
         lib.mc_oracle_run.restype = ctypes.c_int
+        lib.mc_oracle_interior_stats.argtypes = [P, P]
+        lib.mc_oracle_interior_stats.restype = None
         _LIB = lib
     return _LIB
 
@@ -58,5 +60,8 @@ def marching_cubes_lewiner(volume, level, return_stats=False):
                       normals.ctypes.data, values.ctypes.data,
                       ctypes.byref(nv), ctypes.byref(nf), ctypes.byref(na))
     if return_stats:
-        return verts, faces, normals, values, {"ambiguous_cells": int(na.value)}
+        ni, nt = ctypes.c_int64(), ctypes.c_int64()
+        lib.mc_oracle_interior_stats(ctypes.byref(ni), ctypes.byref(nt))
+        return verts, faces, normals, values, {"ambiguous_cells": int(na.value), "interior_ambiguous_cells": int(ni.value),
+                                               "tunnel_cells": int(nt.value)}
     return verts, faces, normals, values

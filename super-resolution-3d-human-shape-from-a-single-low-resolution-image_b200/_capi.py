@@ -53,6 +53,7 @@ SIGNATURES = {
     "surs_octree_select": (ctypes.c_int, [_P, _P, ctypes.c_int, _P, _P, _P, _P]),
     "surs_octree_cells": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_double, _P, _P, _P, _P]),
     "surs_mc_count": (ctypes.c_int, [_P, _P, _P, ctypes.c_float, ctypes.c_int, _P, _P, _P, _P]),
+    "surs_mc_interior_stats": (ctypes.c_int, [_P, _P, _P]),
     "surs_mc_emit": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "surs_mc_emit_verts": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, ctypes.c_int, _P, _P]),
     "surs_mc_emit_faces": (ctypes.c_int, [_P, _P, _P, _P]),
@@ -186,6 +187,12 @@ class Context:
         n, d, b, f = _I64(0), ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int(0)
         self.lib.surs_refine_stats(self._h, ctypes.byref(n), ctypes.byref(d), ctypes.byref(b), ctypes.byref(f))
         return {"nodes": int(n.value), "max_diff": float(d.value), "band": float(b.value), "fell_back": bool(f.value)}
+
+    def mc_interior_stats(self):
+        """(cells with an interior ambiguity, cells that took the tunnel triangulation) of the last mc_count."""
+        a, b = _I64(0), _I64(0)
+        self._check(self.lib.surs_mc_interior_stats(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
 
     def mc_seam_violations(self):
         """Seam edges without a vertex id in the last mc_emit_faces (0 unless two slabs disagree on a shared plane)."""

@@ -11,7 +11,7 @@
 //     (mc_edge_rank, generated with the case tables),
 //   * prefix sums over cells in scan order give the global numbering.
 // Kernels: count (per-block totals) -> scan of block totals -> emit vertices (+ edge->id map)
-// -> emit faces.  Case tables: csrc/mc_tables.h (derivation in oracle/gen_mc_tables.py).
+// -> emit faces.  Case tables: csrc/mc_tables.h (derivation in csrc/gen_mc_tables.py).
 #include "common.cuh"
 #include "mc_tables.h"
 
@@ -29,6 +29,11 @@ struct McTables {
     const uint16_t *tri_off;     // [E]
     const uint8_t *tri_edges;    // [3*T]
     const uint8_t *edge_rank;    // [E][13]
+    const uint8_t *ntest;        // [E] interior (tunnel) tests of the entry
+    const uint16_t *test_off;    // [E]
+    const uint8_t *test_corners; // [T][8]
+    const uint8_t *test_sign;    // [T]
+    const uint16_t *test_target; // [T]
 };
 
 __constant__ uint8_t c_corner_off[24];
@@ -50,8 +55,31 @@ struct Cell {
     unsigned owned;     // 13-bit mask of vertex slots this cell creates
     int nv, nt;
     int ambiguous;
+    int interior;       // 0: no interior ambiguity, 1: interior test(s) evaluated, all failed, 2: tunnel variant taken
     double d[8];
 };
+
+// Interior (tunnel) test, csrc/gen_mc_tables.py: the regions on the lines A and C (cube edges parallel to one axis,
+// cyclic order A B C D) are joined through the cell iff the section at the stationary point of q(t) = At Ct - Bt Dt
+// has At, Ct of sign s and q > 0.  Same operation order as oracle/mc_oracle.c and the generator (no contraction).
+__device__ __forceinline__ bool interior_test(const double (&d)[8], const uint8_t *cn, int s)
+{
+    const double a0 = d[cn[0]], a1 = d[cn[1]], b0 = d[cn[2]], b1 = d[cn[3]], c0 = d[cn[4]], c1 = d[cn[5]], d0 = d[cn[6]], d1 = d[cn[7]];
+    const double dA = __dsub_rn(a1, a0), dB = __dsub_rn(b1, b0), dC = __dsub_rn(c1, c0), dD = __dsub_rn(d1, d0);
+    const double qa = __dsub_rn(__dmul_rn(dA, dC), __dmul_rn(dB, dD));
+    const double qb = __dsub_rn(__dadd_rn(__dmul_rn(a0, dC), __dmul_rn(c0, dA)), __dadd_rn(__dmul_rn(b0, dD), __dmul_rn(d0, dB)));
+    if (!(qa < 0.0)) return false;
+    const double t = __ddiv_rn(-qb, __dmul_rn(2.0, qa));
+    if (!(t > 0.0 && t < 1.0)) return false;
+    const double At = __dadd_rn(a0, __dmul_rn(dA, t)), Bt = __dadd_rn(b0, __dmul_rn(dB, t));
+    const double Ct = __dadd_rn(c0, __dmul_rn(dC, t)), Dt = __dadd_rn(d0, __dmul_rn(dD, t));
+    if (s) {
+        if (!(At > 0.0 && Ct > 0.0)) return false;
+    } else if (At > 0.0 || Ct > 0.0) {
+        return false;
+    }
+    return __dsub_rn(__dmul_rn(At, Ct), __dmul_rn(Bt, Dt)) > 0.0;
+}
 
 __device__ __forceinline__ int64_t node_lin(const McParams &p, int i, int j, int k) { return ((int64_t)i * p.R1 + j) * p.R2 + k; }
 
@@ -59,7 +87,7 @@ __device__ __forceinline__ void classify_vals(const McParams &p, int i, int j, i
 
 __device__ __forceinline__ void classify(const McParams &p, int i, int j, int k, Cell &c)
 {
-    c.entry = -1; c.nv = 0; c.nt = 0; c.owned = 0; c.ambiguous = 0;
+    c.entry = -1; c.nv = 0; c.nt = 0; c.owned = 0; c.ambiguous = 0; c.interior = 0;
     if (i >= p.R0 - 1 || j >= p.R1 - 1 || k >= p.R2 - 1) return;
     float val[8];
 #pragma unroll
@@ -71,7 +99,7 @@ __device__ __forceinline__ void classify(const McParams &p, int i, int j, int k,
 // val[q] = volume value at corner q of cell (i,j,k) (which must be a valid cell)
 __device__ __forceinline__ void classify_vals(const McParams &p, int i, int j, int k, const float (&val)[8], Cell &c)
 {
-    c.entry = -1; c.nv = 0; c.nt = 0; c.owned = 0; c.ambiguous = 0;
+    c.entry = -1; c.nv = 0; c.nt = 0; c.owned = 0; c.ambiguous = 0; c.interior = 0;
     unsigned cas = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -94,6 +122,17 @@ __device__ __forceinline__ void classify_vals(const McParams &p, int i, int j, i
         }
     }
     c.entry = (int)p.tb.var_base[cas] + (int)var;
+    const int ntest = p.tb.ntest[c.entry];
+    if (ntest) {                                   // rare: two same-sign regions that a tunnel through the cell may join
+        c.interior = 1;
+        const int t0 = p.tb.test_off[c.entry];
+        for (int q = 0; q < ntest; ++q)
+            if (interior_test(c.d, p.tb.test_corners + 8 * (t0 + q), p.tb.test_sign[t0 + q])) {
+                c.entry = p.tb.test_target[t0 + q];
+                c.interior = 2;
+                break;
+            }
+    }
     c.nt = p.tb.ntri[c.entry];
     // ownership: offset 1 in both transverse axes, or offset 0 where the cell index is 0
     const int idx[3] = {i, j, k};
@@ -150,7 +189,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McParams p, int64_
 {
     const int64_t lin = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
     Cell c;
-    c.nv = c.nt = 0; c.ambiguous = 0;
+    c.nv = c.nt = 0; c.ambiguous = 0; c.interior = 0;
     if (lin < nnode) {
         int i, j, k;
         cell_coords(p, lin, i, j, k);
@@ -158,6 +197,8 @@ __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McParams p, int64_
     }
     unsigned ea, eb, ta, tb;
     block_scan2((unsigned)c.nv, (unsigned)c.nt, ea, eb, ta, tb);
+    if (c.interior) atomicAdd(n_amb + 8, 1ull);                 // counter[9]: cells with an interior ambiguity
+    if (c.interior == 2) atomicAdd(n_amb + 9, 1ull);            // counter[10]: ... that took the tunnel variant
     const unsigned amb = __syncthreads_count(c.ambiguous);
     if (threadIdx.x == 0) {
         block_tot[blockIdx.x] = make_uint2(ta, tb);
@@ -504,7 +545,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_cell_kernel(McParams p, CellRec
 {
     const uint32_t a = blockIdx.x * MC_THREADS + threadIdx.x;
     Cell c;
-    c.nv = 0; c.nt = 0; c.ambiguous = 0;
+    c.nv = 0; c.nt = 0; c.ambiguous = 0; c.interior = 0;
     if (a < nact) {
         int i, j, k;
         cell_coords(p, (int64_t)cells[a].lin, i, j, k);
@@ -515,6 +556,8 @@ __global__ void __launch_bounds__(MC_THREADS) mc_cell_kernel(McParams p, CellRec
     if (a < nact) { cells[a].vbase = ev; cells[a].fbase = ef; }
     if (threadIdx.x == 0) block_tot[blockIdx.x] = make_uint4(0, tv, tf, 0);
     if (c.ambiguous) atomicAdd(n_amb, 1ull);
+    if (c.interior) atomicAdd(n_amb + 8, 1ull);
+    if (c.interior == 2) atomicAdd(n_amb + 9, 1ull);
 }
 
 __global__ void __launch_bounds__(1024) mc_scan_blocks3_kernel(uint4 *block_tot, int64_t nblocks, unsigned long long *totals)
@@ -588,6 +631,11 @@ struct TableBlob {
     uint16_t tri_off[MC_NUM_ENTRIES];
     uint8_t tri_edges[MC_NUM_TRI_IDX];
     uint8_t edge_rank[MC_NUM_ENTRIES * 13];
+    uint8_t ntest[MC_NUM_ENTRIES];
+    uint16_t test_off[MC_NUM_ENTRIES];
+    uint8_t test_corners[MC_NUM_TESTS * 8];
+    uint8_t test_sign[MC_NUM_TESTS];
+    uint16_t test_target[MC_NUM_TESTS];
 };
 
 McParams make_params(surs_ctx *ctx)
@@ -600,6 +648,8 @@ McParams make_params(surs_ctx *ctx)
     const TableBlob *b = (const TableBlob *)ctx->mc_tables;
     p.tb.amb_mask = b->amb_mask; p.tb.var_base = b->var_base; p.tb.ntri = b->ntri;
     p.tb.tri_off = b->tri_off; p.tb.tri_edges = b->tri_edges; p.tb.edge_rank = b->edge_rank;
+    p.tb.ntest = b->ntest; p.tb.test_off = b->test_off; p.tb.test_corners = b->test_corners;
+    p.tb.test_sign = b->test_sign; p.tb.test_target = b->test_target;
     return p;
 }
 
@@ -614,6 +664,11 @@ int surs_mc_init_tables(surs_ctx *ctx)
     memcpy(h->tri_off, mc_tri_off, sizeof(h->tri_off));
     memcpy(h->tri_edges, mc_tri_edges, sizeof(h->tri_edges));
     memcpy(h->edge_rank, mc_edge_rank, sizeof(h->edge_rank));
+    memcpy(h->ntest, mc_ntest, sizeof(h->ntest));
+    memcpy(h->test_off, mc_test_off, sizeof(h->test_off));
+    memcpy(h->test_corners, mc_test_corners, sizeof(h->test_corners));
+    memcpy(h->test_sign, mc_test_sign, sizeof(h->test_sign));
+    memcpy(h->test_target, mc_test_target, sizeof(h->test_target));
     cudaError_t e = cudaMalloc(&ctx->mc_tables, sizeof(TableBlob));
     if (e == cudaSuccess) e = cudaMemcpy(ctx->mc_tables, h, sizeof(TableBlob), cudaMemcpyHostToDevice);
     delete h;
@@ -640,6 +695,8 @@ extern "C" int surs_mc_count(surs_ctx *ctx, const float *vol, const int res[3], 
     ctx->mc_level = level;
     ctx->mc_flags = flags;
     SURS_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, 64, st));
+    SURS_CUDA(ctx, cudaMemsetAsync(ctx->counter + 9, 0, 16, st));
+    ctx->mc_count_stream = st;
     McParams p = make_params(ctx);
     static const bool no_fast = getenv("SURS_MC_SLOW") != nullptr;
     ctx->mc_fast = (res[2] % 4 == 0) && ((uintptr_t)vol % 16 == 0) && !no_fast;
@@ -769,6 +826,18 @@ extern "C" int surs_mc_emit_faces(surs_ctx *ctx, int32_t *faces, const int32_t *
                                                                       seam_in, ctx->mc_id_offset, faces, ctx->counter + 8);
         SURS_LAUNCH_CHECK(ctx, "mc_emit_faces_kernel");
     }
+    return 0;
+}
+
+extern "C" int surs_mc_interior_stats(surs_ctx *ctx, int64_t *n_interior_ambiguous, int64_t *n_tunnels)
+{
+    if (!ctx) return 1;
+    unsigned long long n[2] = {0, 0};
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    SURS_CUDA(ctx, cudaMemcpyAsync(n, ctx->counter + 9, sizeof(n), cudaMemcpyDeviceToHost, (cudaStream_t)ctx->mc_count_stream));
+    SURS_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)ctx->mc_count_stream));
+    if (n_interior_ambiguous) *n_interior_ambiguous = (int64_t)n[0];
+    if (n_tunnels) *n_tunnels = (int64_t)n[1];
     return 0;
 }
 

@@ -270,6 +270,35 @@ def test_marching_cubes_matches_cpu_twin(ctx):
     _mc_check(ctx, np.ascontiguousarray(vol[23:25]))                    # minimal thickness
 
 
+def test_marching_cubes_passes_the_table_free_checker(ctx):
+    """The kernels' meshes against the VOLUME alone (oracle/mc_check.py reads no table): vertex placement, one cell per
+    triangle, closed oriented manifold, and the topology of the ambiguous cells (face deciders + interior / tunnel test)
+    against the trilinear interpolant; interior statistics equal the CPU twin's."""
+    from oracle import mc_check
+    rng = np.random.default_rng(4)
+    vol = rng.random((12, 9, 16)).astype(np.float32)
+    gv, _, gf, _, _, namb = ctx.marching_cubes(torch.from_numpy(vol).to(ctx.device), 0.5)
+    n_int, n_tun = ctx.mc_interior_stats()
+    v, f, _, _, st = mc_oracle.marching_cubes_lewiner(vol, 0.5, return_stats=True)
+    assert np.array_equal(gv.cpu().numpy(), v) and np.array_equal(gf.cpu().numpy(), f)
+    assert (namb, n_int, n_tun) == (st["ambiguous_cells"], st["interior_ambiguous_cells"], st["tunnel_cells"])
+    assert n_int > 50 and n_tun > 0
+    rep = mc_check.check_mesh(vol, 0.5, gv.cpu().numpy(), gf.cpu().numpy())
+    top = mc_check.check_cell_topology(vol, 0.5, gv.cpu().numpy(), gf.cpu().numpy(), max_cells=200)
+    print(rep, {k: top[k] for k in top if k != "mismatches"})
+    assert top["cells_checked"] > 100 and top["mismatch"] == 0, top["mismatches"]
+    # general (non-fast) kernels: last axis not a multiple of 4
+    vol2 = np.ascontiguousarray(vol[:, :, :15])
+    gv, _, gf, _, _, _ = ctx.marching_cubes(torch.from_numpy(vol2).to(ctx.device), 0.5)
+    assert ctx.mc_interior_stats() == tuple(mc_oracle.marching_cubes_lewiner(vol2, 0.5, return_stats=True)[4][k] for k in ("interior_ambiguous_cells", "tunnel_cells"))
+    mc_check.check_mesh(vol2, 0.5, gv.cpu().numpy(), gf.cpu().numpy())
+    # a smooth closed surface: every check, no tolerance on orientation
+    sph = helpers.sphere_volume(32, 10.2)
+    gv, _, gf, _, _, _ = ctx.marching_cubes(torch.from_numpy(sph).to(ctx.device), 0.5)
+    rep = mc_check.check_mesh(sph, 0.5, gv.cpu().numpy(), gf.cpu().numpy())
+    assert rep["orientation_wrong"] == 0 and rep["border_edges"] == 0
+
+
 def test_marching_cubes_slabs_reproduce_single_volume(ctx):
     """Three slabs with the seam protocol (SURS_MC_LOWER_FOREIGN + seam maps) == one volume."""
     from surs_b200 import _capi
