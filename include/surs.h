@@ -95,6 +95,26 @@ int surs_set_features(surs_ctx *ctx, const float *f_lr, int C_lr, int H_lr, int 
 int surs_set_features_host(surs_ctx *ctx, const float *f_lr, int C_lr, int H_lr, int W_lr,
                            const float *f_hr, int C_hr, int H_hr, int W_hr, float u_lo, float u_hi, void *stream);
 
+/* Projection variant used by every following surs_query* / surs_eval_grid* call of this context.
+ * Replaces: the `projection_mode` of lib/model/SuRSNet.py:44-57 -- perspective = 0: lib/geometry.py:15-31 `orthogonal`
+ * (default), 1: :34-48 `perspective` ((u, v) = (R p + t).xy / (R p + t).z) -- and the optional image-space
+ * `transforms` argument of query_mr / query_sr (lib/geometry.py:27-30,43-46): transform [host] = 2x3 row-major
+ * [scale | shift], (u, v) <- scale (u, v) + shift, applied before the in-image test; NULL = none.
+ * Column-factored grids need the orthogonal projection (any transform is fine); perspective grids take the
+ * generic kernels. */
+int surs_set_projection(surs_ctx *ctx, int perspective, const float *transform);
+
+/* Multi-view (opt.num_views > 1).  Replaces: lib/model/SurfaceClassifier.py:70-76 -- after layer 2 the activations
+ * and the skip input are averaged over the views of a subject -- together with the per-view projection / indexing of
+ * lib/model/SuRSNet.py:131-187.  f_lr [dev] NCHW fp32 [V,256,H,W], f_hr [dev] [V,64,H,W]; pts [dev] fp32 [V,3,N]
+ * (the reference repeats the same points per view, lib/mesh_util.py:22), calibs [host] V x (upper 3x4, row-major).
+ * pred_hr / pred_lr [dev] fp32 [V,N]: mask_v x sigmoid(...), as the reference's [V,1,N] predictions.
+ * Runs the fp32 CUDA-core kernel (exact mode) whatever the precision of the single-view calls. */
+int surs_set_features_views(surs_ctx *ctx, int n_views, const float *f_lr, int C_lr, int H_lr, int W_lr,
+                            const float *f_hr, int C_hr, int H_hr, int W_hr, void *stream);
+int surs_query_views(surs_ctx *ctx, const float *pts, int64_t n, const float *calibs, float z_num, float z_den,
+                     float *pred_hr, float *pred_lr, void *stream);
+
 /* Replaces: SuRSNet.query_mr + query_sr + get_preds (lib/model/SuRSNet.py:131-187,
  * lib/model/BaseSuRSNet.py:80-85) with lib/geometry.py:15-31 `orthogonal`, :4-12 `index`,
  * lib/model/DepthNormalizer.py:18 and lib/model/SurfaceClassifier.py:45-81 fused.

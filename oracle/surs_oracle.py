@@ -37,6 +37,22 @@ def orthogonal(points, calib):
     return xyz.astype(np.float32)
 
 
+def project(points, calib, perspective=False, uv_transform=None):
+    """lib/geometry.py:15-31 `orthogonal` / :34-48 `perspective`, with the optional image-space affine `transforms`
+    (:27-30,43-46: (u, v) <- scale (u, v) + shift with [scale | shift] = transforms[:2, :3]).  float32 result.
+    NB the reference's own `transforms` branch cannot run (it indexes a 2-D matrix and hands it to baddbmm, which wants
+    3-D operands); this restates its evident intent, PIFu's 2x3 affine."""
+    xyz = orthogonal(points, calib).astype(np.float64)
+    if perspective:
+        xy = (xyz[:2].astype(np.float32) / xyz[2:3].astype(np.float32)).astype(np.float64)
+    else:
+        xy = xyz[:2]
+    if uv_transform is not None:
+        t = np.asarray(uv_transform, dtype=np.float32).astype(np.float64)[:2, :3]
+        xy = (t[:, :2] @ xy + t[:, 2:3])
+    return np.concatenate([xy, xyz[2:3]], axis=0).astype(np.float32)
+
+
 def in_image_mask(xyz):
     """lib/model/SuRSNet.py:142 -- inclusive on both ends, float32 compare."""
     u, v = xyz[0], xyz[1]
@@ -104,14 +120,57 @@ def surface_classifier(weights, biases, feature, res_layers=(2, 3, 4), no_residu
 # ----------------------------------------------------------------------------
 # L1: query_mr + query_sr + get_preds
 # ----------------------------------------------------------------------------
+def surface_classifier_views(weights, biases, features, res_layers=(2, 3, 4)):
+    """lib/model/SurfaceClassifier.py:45-81 with num_views = V > 1 (one subject): features [V,C0,N]; after layer
+    len(filters) // 2 = 2 (and its leaky ReLU) y and the skip input are averaged over the views (:70-76)."""
+    feats = np.asarray(features, dtype=np.float64)
+    V = feats.shape[0]
+    ys = [feats[v] for v in range(V)]
+    fs = [feats[v] for v in range(V)]
+    n = len(weights)
+    for i in range(n):
+        w = np.asarray(weights[i], dtype=np.float64)
+        b = np.asarray(biases[i], dtype=np.float64)
+        out = []
+        for y, f in zip(ys, fs):
+            x = np.concatenate([y, f], axis=0) if i in res_layers else y
+            y = w @ x + b[:, None]
+            if i != n - 1:
+                y = leaky_relu(y)
+            out.append(y)
+        ys = out
+        if i == n // 2 and len(ys) > 1:
+            ys = [np.mean(np.stack(ys), axis=0)]
+            fs = [np.mean(np.stack(fs), axis=0)]
+    return 1.0 / (1.0 + np.exp(-ys[0]))
+
+
+def query_views(points, calibs, feats_lr, feats_hr, mlp_lr, mlp_hr, load_size=512, z_size=200.0, perspective=False, uv_transform=None):
+    """lib/model/SuRSNet.py:131-187 with num_views = V views of one subject: points [V,3,N] (the same points repeated,
+    lib/mesh_util.py:22), calibs [V,4,4], feats_lr [V,256,H,W], feats_hr [V,64,H,W] -> (pred_hr, pred_lr) [V,N]."""
+    V = len(calibs)
+    f321, masks = [], []
+    for v in range(V):
+        xyz = project(points[v], calibs[v], perspective, uv_transform)
+        masks.append(in_image_mask(xyz).astype(np.float64))
+        zf = depth_feature(xyz[2], load_size, z_size).astype(np.float64)
+        u, w = xyz[0].astype(np.float64), xyz[1].astype(np.float64)
+        f321.append(np.concatenate([index(feats_lr[v], u, w), index(feats_hr[v], u, w), zf[None, :]], axis=0))
+    masks = np.stack(masks)
+    pred_lr = masks * surface_classifier_views(mlp_lr[0], mlp_lr[1], np.stack(f321))[0][None, :]
+    f322 = np.stack([np.concatenate([f321[v], pred_lr[v][None, :]], axis=0) for v in range(V)])
+    pred_hr = masks * surface_classifier_views(mlp_hr[0], mlp_hr[1], f322)[0][None, :]
+    return pred_hr, pred_lr
+
+
 def query(points, calib, feat_lr, feat_hr, mlp_lr, mlp_hr, load_size=512, z_size=200.0,
-          res_layers=(2, 3, 4), return_features=False):
+          res_layers=(2, 3, 4), return_features=False, perspective=False, uv_transform=None):
     """lib/model/SuRSNet.py:131-187 + lib/model/BaseSuRSNet.py:80-85 (num_views == 1).
 
     points [3,N]; feat_lr [256,Hl,Wl], feat_hr [64,Hh,Wh]; mlp_* = (weights, biases).
     Returns (pred_hr, pred_lr) float64 [N] -- HR first, as get_preds does.
     """
-    xyz = orthogonal(points, calib)
+    xyz = project(points, calib, perspective, uv_transform)
     mask = in_image_mask(xyz).astype(np.float64)
     zf = depth_feature(xyz[2], load_size, z_size).astype(np.float64)
     u = xyz[0].astype(np.float64)

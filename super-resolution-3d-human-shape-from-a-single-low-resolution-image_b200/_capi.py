@@ -43,6 +43,10 @@ SIGNATURES = {
                                          _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
     "surs_set_features_host": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, _P]),
+    "surs_set_projection": (ctypes.c_int, [_P, ctypes.c_int, _P]),
+    "surs_set_features_views": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
+    "surs_query_views": (ctypes.c_int, [_P, _P, _I64, _P, ctypes.c_float, ctypes.c_float, _P, _P, _P]),
     "surs_query": (ctypes.c_int, [_P, _P, _I64, _P, ctypes.c_float, ctypes.c_float, ctypes.c_int, _P, _P, _P]),
     "surs_query_host": (ctypes.c_int, [_P, _P, _I64, _P, ctypes.c_float, ctypes.c_float, ctypes.c_int, _P, _P, _P]),
     "surs_eval_grid": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_int,
@@ -173,6 +177,41 @@ class Context:
                                                    _ptr(f_hr), f_hr.shape[0], f_hr.shape[1], f_hr.shape[2], _stream(self.device)))
             torch.cuda.current_stream(self.device).synchronize()   # inputs are borrowed until the repack ran
         self.feature_generation += 1
+
+    # ---- projection variant / multi-view ------------------------------------------------
+    def set_projection(self, perspective=False, uv_transform=None):
+        """Projection used by the following query / grid calls: orthogonal (lib/geometry.py:15-31) or perspective
+        (:34-48), plus the optional image-space `transforms` [2,3] (or [3,3]) of query_mr / query_sr."""
+        tf = None
+        if uv_transform is not None:
+            t = uv_transform.detach().to("cpu", torch.float32).numpy() if isinstance(uv_transform, torch.Tensor) else np.asarray(uv_transform, np.float32)
+            tf = np.ascontiguousarray(t.reshape(-1, t.shape[-1])[:2, :3], dtype=np.float32)
+        self._check(self.lib.surs_set_projection(self._h, int(bool(perspective)), None if tf is None else tf.ctypes.data))
+
+    def set_features_views(self, f_lr, f_hr):
+        """Multi-view maps: f_lr [V,256,H,W], f_hr [V,64,H,W] fp32 NCHW on the device."""
+        f_lr = f_lr.detach().to(self.device, torch.float32).contiguous()
+        f_hr = f_hr.detach().to(self.device, torch.float32).contiguous()
+        if f_lr.dim() != 4 or f_hr.dim() != 4 or f_lr.shape[0] != f_hr.shape[0]:
+            raise RuntimeError("set_features_views takes [V,C,H,W] maps with the same number of views")
+        with torch.cuda.device(self.device):
+            self._check(self.lib.surs_set_features_views(self._h, f_lr.shape[0], _ptr(f_lr), f_lr.shape[1], f_lr.shape[2], f_lr.shape[3],
+                                                         _ptr(f_hr), f_hr.shape[1], f_hr.shape[2], f_hr.shape[3], _stream(self.device)))
+            torch.cuda.current_stream(self.device).synchronize()
+        self.n_views = int(f_lr.shape[0])
+
+    def query_views(self, points, calibs, z_num, z_den):
+        """points [V,3,N] fp32 on the device, calibs [V,4,4] / [V,3,4] -> (pred_hr, pred_lr) fp32 [V,N] (fp32 kernel)."""
+        pts = points.detach().to(self.device, torch.float32).contiguous()
+        V, n = pts.shape[0], pts.shape[2]
+        c = calibs.detach().to("cpu", torch.float32).numpy() if isinstance(calibs, torch.Tensor) else np.asarray(calibs, np.float32)
+        c = np.ascontiguousarray(c.reshape(V, -1, 4)[:, :3, :4], dtype=np.float32)
+        hr = torch.empty((V, n), device=self.device, dtype=torch.float32)
+        lr = torch.empty((V, n), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.surs_query_views(self._h, _ptr(pts), n, c.ctypes.data, float(z_num), float(z_den), _ptr(hr), _ptr(lr),
+                                                  _stream(self.device)))
+        return hr, lr
 
     # ---- query ----------------------------------------------------------------------
     @property

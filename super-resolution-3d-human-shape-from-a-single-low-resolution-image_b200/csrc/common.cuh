@@ -39,6 +39,9 @@ struct PointIO {
     // projection / depth
     float calib[12];
     float z_num, z_den;
+    int persp;                 // 1: lib/geometry.py:34-48 `perspective` (xy / z), 0: :15-31 `orthogonal`
+    int has_tf;                // image-space affine `transforms` (lib/geometry.py:27-30,43-46): (u, v) <- tf[:, :2] (u, v) + tf[:, 2]
+    float tf[6];
     // outputs
     float *out_hr, *out_lr;    // fp32, index n (explicit / dense slab)
     double *vol_hr, *vol_lr;   // float64 volumes, index = node (octree scatter); used when non-NULL
@@ -95,16 +98,29 @@ __device__ __forceinline__ void pointio_store(const PointIO &io, int64_t n, floa
 struct Projected {
     float u, v, zf, mask;
 };
-__device__ __forceinline__ Projected project_point(const PointIO &io, float x, float y, float z)
+__device__ __forceinline__ Projected project_core(const float *c, float z_num, float z_den, int persp, int has_tf, const float *tf,
+                                                  float x, float y, float z)
 {
-    const float *c = io.calib;
     Projected p;
     p.u = fmaf(c[2], z, fmaf(c[1], y, fmaf(c[0], x, c[3])));
     p.v = fmaf(c[6], z, fmaf(c[5], y, fmaf(c[4], x, c[7])));
     float zz = fmaf(c[10], z, fmaf(c[9], y, fmaf(c[8], x, c[11])));
+    if (persp) {                                       // lib/geometry.py:41: xy = homo[:, :2] / homo[:, 2:3]
+        p.u = __fdiv_rn(p.u, zz);
+        p.v = __fdiv_rn(p.v, zz);
+    }
+    if (has_tf) {                                      // lib/geometry.py:27-30 / 43-46: baddbmm(shift, scale, xy)
+        const float u = p.u, v = p.v;
+        p.u = fmaf(tf[1], v, fmaf(tf[0], u, tf[2]));
+        p.v = fmaf(tf[4], v, fmaf(tf[3], u, tf[5]));
+    }
     p.mask = (p.u >= -1.0f && p.u <= 1.0f && p.v >= -1.0f && p.v <= 1.0f) ? 1.0f : 0.0f;
-    p.zf = __fdiv_rn(__fmul_rn(zz, io.z_num), io.z_den);
+    p.zf = __fdiv_rn(__fmul_rn(zz, z_num), z_den);
     return p;
+}
+__device__ __forceinline__ Projected project_point(const PointIO &io, float x, float y, float z)
+{
+    return project_core(io.calib, io.z_num, io.z_den, io.persp, io.has_tf, io.tf, x, y, z);
 }
 
 // grid_sample(align_corners=True, bilinear, zeros) tap set-up (lib/geometry.py:11)
@@ -161,6 +177,14 @@ struct surs_ctx {
     void *col_table;                       // per-column vectors (query_col.cu)
     size_t col_table_cap;
     float tc_w4y[2][128];                  // W4[0, 0:128] of both MLPs (host copy, passed as kernel parameter)
+    // ---- projection variant used by the following query / grid calls (surs_set_projection) ----
+    int persp, has_tf;
+    float tf[6];
+    // ---- multi-view features (surs_set_features_views): [V][H][W][C] fp32, channels-last ----
+    int mv_views;
+    float *mv_f_lr32, *mv_f_hr32;
+    size_t mv_lr_cap, mv_hr_cap;
+    int mv_H_lr, mv_W_lr, mv_H_hr, mv_W_hr;
     // ---- features, channels-last ------------------------------------------------
     int have_features;
     int H_lr, W_lr, H_hr, W_hr;
@@ -233,6 +257,8 @@ int surs_ensure(surs_ctx *ctx, void **ptr, size_t *cap, size_t bytes);
 
 // query_simt.cu
 int surs_launch_query_simt(surs_ctx *ctx, const PointIO &io, cudaStream_t st);
+int surs_launch_query_simt_views(surs_ctx *ctx, const float *pts, int64_t n, const float *calibs, float z_num, float z_den,
+                                 float *pred_hr, float *pred_lr, cudaStream_t st);
 // query_tc.cu
 int surs_tc_pack_weights(surs_ctx *ctx, const float *const w[2][SURS_NUM_LAYERS], cudaStream_t st);
 int surs_launch_query_tc(surs_ctx *ctx, const PointIO &io, cudaStream_t st);

@@ -3,7 +3,7 @@
 
 Why generated: the reference's marching cubes is scikit-image 0.17.2's
 ``marching_cubes_lewiner`` (lib/mesh_util.py:40,45), a third-party Cython module
-that is neither vendored in /root/reference nor installed here, and Lewiner's
+that is neither vendored in the reference tree nor installed here, and Lewiner's
 hand-made 33-case tables are not available offline.  Instead of recalling ~2k
 lines of tables, the triangulation is *derived*:
 

@@ -73,6 +73,7 @@ extern "C" void surs_destroy(surs_ctx *ctx)
     cudaFree(ctx->col_weights);
     cudaFree(ctx->col_weights_x3);
     cudaFree(ctx->col_table);
+    cudaFree(ctx->mv_f_lr32); cudaFree(ctx->mv_f_hr32);
     cudaFree(ctx->f_lr32); cudaFree(ctx->f_hr32); cudaFree(ctx->f_lr16); cudaFree(ctx->f_hr16); cudaFree(ctx->feat_stage);
     cudaFree(ctx->axis_dev); cudaFree(ctx->dirty); cudaFree(ctx->idx_list); cudaFree(ctx->counter);
     cudaFree(ctx->stage_pts); cudaFree(ctx->stage_out);
@@ -308,11 +309,23 @@ static int run_query(surs_ctx *ctx, const PointIO &io, int precision, cudaStream
     return precision == SURS_PREC_FP16 ? surs_launch_query_tc(ctx, io, st) : surs_launch_query_simt(ctx, io, st);
 }
 
-static void fill_proj(PointIO &io, const float calib[12], float z_num, float z_den)
+static void fill_proj(const surs_ctx *ctx, PointIO &io, const float calib[12], float z_num, float z_den)
 {
     memcpy(io.calib, calib, sizeof(float) * 12);
     io.z_num = z_num;
     io.z_den = z_den;
+    io.persp = ctx->persp;
+    io.has_tf = ctx->has_tf;
+    memcpy(io.tf, ctx->tf, sizeof(io.tf));
+}
+
+extern "C" int surs_set_projection(surs_ctx *ctx, int perspective, const float *transform)
+{
+    if (!ctx) return 1;
+    ctx->persp = perspective ? 1 : 0;
+    ctx->has_tf = transform != nullptr;
+    if (transform) memcpy(ctx->tf, transform, sizeof(ctx->tf));
+    return 0;
 }
 
 extern "C" int surs_query(surs_ctx *ctx, const float *pts, int64_t n, const float calib[12],
@@ -325,8 +338,55 @@ extern "C" int surs_query(surs_ctx *ctx, const float *pts, int64_t n, const floa
     PointIO io;
     memset(&io, 0, sizeof(io));
     io.pts = pts; io.n = n; io.out_hr = pred_hr; io.out_lr = pred_lr;
-    fill_proj(io, calib, z_num, z_den);
+    fill_proj(ctx, io, calib, z_num, z_den);
     return run_query(ctx, io, precision, (cudaStream_t)stream);
+}
+
+// NCHW fp32 -> NHWC fp32 only (multi-view maps feed the fp32 kernel)
+__global__ void repack32_kernel(const float *__restrict__ src, float *__restrict__ dst32, int C, int HW)
+{
+    __shared__ float tile[32][33];
+    int px = blockIdx.x * 32 + threadIdx.x, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8)
+        if (c0 + i < C && px < HW) tile[i][threadIdx.x] = src[(size_t)(c0 + i) * HW + px];
+    __syncthreads();
+    int c = c0 + threadIdx.x, p0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += 8)
+        if (p0 + i < HW && c < C) dst32[(size_t)(p0 + i) * C + c] = tile[threadIdx.x][i];
+}
+
+extern "C" int surs_set_features_views(surs_ctx *ctx, int n_views, const float *f_lr, int C_lr, int H_lr, int W_lr,
+                                       const float *f_hr, int C_hr, int H_hr, int W_hr, void *stream)
+{
+    if (!ctx) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_views < 1 || n_views > 16) SURS_FAIL(ctx, "surs_set_features_views: 1..16 views");
+    if (C_lr != SURS_C_LR || C_hr != SURS_C_HR || !f_lr || !f_hr || H_lr < 2 || W_lr < 2 || H_hr < 2 || W_hr < 2)
+        SURS_FAIL(ctx, "surs_set_features_views: expected [V,%d,H,W] and [V,%d,H,W] maps", SURS_C_LR, SURS_C_HR);
+    const size_t n_lr = (size_t)H_lr * W_lr * C_lr, n_hr = (size_t)H_hr * W_hr * C_hr;
+    if (surs_ensure(ctx, (void **)&ctx->mv_f_lr32, &ctx->mv_lr_cap, n_lr * n_views * sizeof(float))) return 1;
+    if (surs_ensure(ctx, (void **)&ctx->mv_f_hr32, &ctx->mv_hr_cap, n_hr * n_views * sizeof(float))) return 1;
+    for (int v = 0; v < n_views; ++v) {
+        repack32_kernel<<<dim3((H_lr * W_lr + 31) / 32, C_lr / 32), dim3(32, 8), 0, st>>>(f_lr + v * n_lr, ctx->mv_f_lr32 + v * n_lr, C_lr, H_lr * W_lr);
+        SURS_LAUNCH_CHECK(ctx, "repack32_kernel(lr)");
+        repack32_kernel<<<dim3((H_hr * W_hr + 31) / 32, C_hr / 32), dim3(32, 8), 0, st>>>(f_hr + v * n_hr, ctx->mv_f_hr32 + v * n_hr, C_hr, H_hr * W_hr);
+        SURS_LAUNCH_CHECK(ctx, "repack32_kernel(hr)");
+    }
+    ctx->mv_views = n_views;
+    ctx->mv_H_lr = H_lr; ctx->mv_W_lr = W_lr; ctx->mv_H_hr = H_hr; ctx->mv_W_hr = W_hr;
+    return 0;
+}
+
+extern "C" int surs_query_views(surs_ctx *ctx, const float *pts, int64_t n, const float *calibs, float z_num, float z_den,
+                                float *pred_hr, float *pred_lr, void *stream)
+{
+    if (!ctx) return 1;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->have_weights) SURS_FAIL(ctx, "surs_set_weights has not been called");
+    if (ctx->mv_views < 1) SURS_FAIL(ctx, "surs_set_features_views has not been called");
+    if (n < 0 || (n > 0 && (!pts || !calibs || !pred_hr || !pred_lr))) SURS_FAIL(ctx, "surs_query_views: bad arguments");
+    return surs_launch_query_simt_views(ctx, pts, n, calibs, z_num, z_den, pred_hr, pred_lr, (cudaStream_t)stream);
 }
 
 extern "C" int surs_query_host(surs_ctx *ctx, const float *pts_host, int64_t n, const float calib[12],
@@ -397,7 +457,7 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
     // image-coordinate range of the slab (extremes of an affine map over a box are at its corners): a stripe of the
     // feature maps (surs_set_features_host) is enough when it covers this range
     float u_lo = -1.0f, u_hi = 1.0f;
-    if (!transform) {
+    if (!transform && !ctx->persp && !ctx->has_tf) {
         double lo[3], hi[3];
         for (int a = 0; a < 3; ++a) {
             const double step = (b_max[a] - b_min[a]) / res[a];
@@ -417,7 +477,7 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
     PointIO io;
     memset(&io, 0, sizeof(io));
     if (setup_grid(ctx, io, res, b_min, b_max, transform, st)) return 1;
-    fill_proj(io, calib, z_num, z_den);
+    fill_proj(ctx, io, calib, z_num, z_den);
     const int64_t plane = (int64_t)res[1] * res[2];
     io.lin_base = plane * plane_lo;
     io.n = plane * (plane_hi - plane_lo);
@@ -429,7 +489,7 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
     // SURS_COL_INC=1: layer 1 by incremental updates along the column (query_inc.cu; exact but, as measured,
     // slower than the GEMM of query_col.cu -- experiments/README.md).  Read per call so that tests can toggle it.
     const bool col_inc = getenv("SURS_COL_INC") != nullptr;
-    if (precision != SURS_PREC_FP32 && !transform && calib[2] == 0.0f && calib[6] == 0.0f && res[2] >= 64 && !no_column) {
+    if (precision != SURS_PREC_FP32 && !transform && !ctx->persp && calib[2] == 0.0f && calib[6] == 0.0f && res[2] >= 64 && !no_column) {
         if (precision == SURS_PREC_FP16X3) return surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st, 3);
         if (precision == SURS_PREC_FP16R) {
             // one pass everywhere, then split operands on the nodes the 0.5 iso-surface can depend on
@@ -579,14 +639,14 @@ extern "C" int surs_eval_grid_octree(surs_ctx *ctx, const int res[3], const doub
     PointIO io;
     memset(&io, 0, sizeof(io));
     if (setup_grid(ctx, io, res, b_min, b_max, transform, st)) return 1;
-    fill_proj(io, calib, z_num, z_den);
+    fill_proj(ctx, io, calib, z_num, z_den);
     io.vol_hr = sdf_hr;
     io.vol_lr = sdf_lr;
     // Column-table path (same preconditions as the dense column kernels): every W.f product once per column,
     // for all levels; the levels then run the indexed variant of query_col_kernel.  SURS_NO_COLUMN=1 disables it.
     if (precision == SURS_PREC_FP16R) precision = SURS_PREC_FP16X3;   // the octree already evaluates near the surface only
     const int passes = precision == SURS_PREC_FP16X3 ? 3 : 1;
-    const bool use_table = precision != SURS_PREC_FP32 && !transform && calib[2] == 0.0f && calib[6] == 0.0f && getenv("SURS_NO_COLUMN") == nullptr;
+    const bool use_table = precision != SURS_PREC_FP32 && !transform && !ctx->persp && calib[2] == 0.0f && calib[6] == 0.0f && getenv("SURS_NO_COLUMN") == nullptr;
     if (use_table) {
         OctPhase ph(ctx, st, OCT_TABLE);
         if (surs_col_build_table(ctx, io, res[1], 0, (int64_t)res[0] * res[1], st, passes)) return 1;

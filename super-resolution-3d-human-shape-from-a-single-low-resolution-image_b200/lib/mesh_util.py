@@ -70,12 +70,14 @@ def _reconstruction(opt, net, cuda, calib_tensor, resolution, b_min, b_max, use_
     b_min = np.asarray(b_min, dtype=np.float64).reshape(3)
     b_max = np.asarray(b_max, dtype=np.float64).reshape(3)
     stats = {}
-    if _is_accelerated(net) and net.can_accelerate(calib_tensor):
+    if _is_accelerated(net) and getattr(net, "num_views", 1) == 1 and net.can_accelerate(calib_tensor):
         ctx = net.surs_context()
         prec = net.precision if precision is None else precision
         mat = grid_matrix(resolution, b_min, b_max, transform)
         res = (resolution,) * 3
         zn, zd = net.depth_scale()
+        persp = getattr(net, "projection_mode", "orthogonal") == "perspective"
+        ctx.set_projection(persp, None)               # perspective grids take the generic kernels (no column structure)
         if use_octree:
             hr64, lr64, n_eval = ctx.eval_grid_octree(res, b_min, b_max, calib_tensor, zn, zd, float(opt.threshold),
                                                       init_resolution=64, transform=transform, precision=prec)
@@ -85,6 +87,7 @@ def _reconstruction(opt, net, cuda, calib_tensor, resolution, b_min, b_max, use_
         else:
             vol_hr, vol_lr = ctx.eval_grid(res, b_min, b_max, calib_tensor, zn, zd, transform=transform, precision=prec)
             stats["n_evaluated"] = int(resolution) ** 3
+        ctx.set_projection(False, None)
     else:
         # generic path of the reference (any net with query_mr / query_sr / get_preds)
         coords, mat = create_grid(resolution, resolution, resolution, b_min, b_max, transform=transform)

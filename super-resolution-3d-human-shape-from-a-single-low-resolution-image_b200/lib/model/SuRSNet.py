@@ -17,9 +17,11 @@ the fused kernel produces both in one launch, so ``query_mr`` runs it and ``quer
 same points returns the cached HR result.  The stray ``print("z", z)`` of
 lib/model/DepthNormalizer.py:17 is intentionally not reproduced.
 
+Covered by the fused kernels as well: image-space ``transforms`` and the perspective projection
+(lib/geometry.py:27-30,34-48; every kernel's projection prologue) and ``num_views > 1`` (the mean over
+views after layer 2, lib/model/SurfaceClassifier.py:70-76; fp32 CUDA-core kernel).
 Not covered by the kernels -> explicit torch path (a warning is issued once, never silent):
-``num_views > 1``, image-space ``transforms``, perspective projection, ``--no_residual``,
-non-default ``mlp_dim`` / ``mlp_res_layers``, training mode (3 hourglass outputs).
+``--no_residual``, non-default ``mlp_dim`` / ``mlp_res_layers``, training mode (3 hourglass outputs).
 """
 import warnings
 
@@ -196,14 +198,19 @@ class SuRSNet(nn.Module):
         return float(self.opt.loadSize // 2), float(self.opt.z_size)
 
     def _kernel_config_ok(self):
-        return (self.num_views == 1 and self.projection_mode == "orthogonal" and not self.opt.no_residual
+        return (self.projection_mode in ("orthogonal", "perspective") and not self.opt.no_residual
                 and list(self.opt.mlp_dim_lr) == _DEFAULT_LR and list(self.opt.mlp_dim_hr) == _DEFAULT_HR
                 and list(self.opt.mlp_res_layers_lr) == [2, 3, 4] and list(self.opt.mlp_res_layers_hr) == [2, 3, 4]
                 and not self.training)
 
     def can_accelerate(self, calibs=None, transforms=None):
-        ok = self._kernel_config_ok() and transforms is None
-        if ok and calibs is not None and torch.is_tensor(calibs) and calibs.dim() == 3 and calibs.shape[0] != 1:
+        """True when the fused CUDA path covers this call: default MLP shapes, eval mode; one view, or ``num_views``
+        views of ONE subject (features / calibs / points with a leading dimension of num_views)."""
+        ok = self._kernel_config_ok()
+        if ok and transforms is not None and not (torch.is_tensor(transforms) and transforms.dim() == 2 and transforms.shape[0] >= 2
+                                                  and transforms.shape[1] == 3):
+            ok = False                                 # the reference indexes transforms[:2, :2] / [:2, 2:3]: one 2-D affine
+        if ok and calibs is not None and torch.is_tensor(calibs) and calibs.dim() == 3 and calibs.shape[0] != self.num_views:
             ok = False
         if ok:
             self._sync()
@@ -226,9 +233,14 @@ class SuRSNet(nn.Module):
         if not self.im_feat_list_lr or not self.im_feat_list_hr:
             raise RuntimeError("image features missing: call filter_lr / filter_hr (or filter) before querying")
         feats = [self.im_feat_list_lr[-1], self.im_feat_list_hr[0]]
+        if self.num_views > 1 and (feats[0].dim() != 4 or feats[0].shape[0] != self.num_views or feats[1].shape[0] != self.num_views):
+            raise RuntimeError("num_views = %d: the feature maps must be [num_views, C, H, W] (one subject)" % self.num_views)
         if (self._f_held is None or self._f_gen_uploaded != self._feat_gen or self._ctx_gen_uploaded != ctx.feature_generation
                 or not self._f_held.same(feats)):
-            ctx.set_features(feats[0], feats[1])
+            if self.num_views > 1:
+                ctx.set_features_views(feats[0], feats[1])
+            else:
+                ctx.set_features(feats[0], feats[1])
             self._f_held = _Held(feats)
             self._f_gen_uploaded, self._ctx_gen_uploaded = self._feat_gen, ctx.feature_generation
             self._q_held = None
@@ -239,12 +251,20 @@ class SuRSNet(nn.Module):
             warnings.warn("surs_b200: %s is not covered by the fused CUDA query; using the torch path" % why)
 
     # ------------------------------------------------------------------ queries
-    def _fused(self, points, calibs):
+    def _fused(self, points, calibs, transforms=None):
         ctx = self.surs_context()
-        pts = points[0] if points.dim() == 3 else points
         zn, zd = self.depth_scale()
-        hr, lr = ctx.query(pts, calibs, zn, zd, precision=self.precision)
-        return hr.view(1, 1, -1), lr.view(1, 1, -1)
+        ctx.set_projection(self.projection_mode == "perspective", transforms)
+        try:
+            if self.num_views > 1:
+                pts = points if points.dim() == 3 else points[None].expand(self.num_views, -1, -1)
+                hr, lr = ctx.query_views(pts, calibs, zn, zd)
+                return hr[:, None, :], lr[:, None, :]
+            pts = points[0] if points.dim() == 3 else points
+            hr, lr = ctx.query(pts, calibs, zn, zd, precision=self.precision)
+            return hr.view(1, 1, -1), lr.view(1, 1, -1)
+        finally:
+            ctx.set_projection(False, None)
 
     def query_mr(self, points, calibs, transforms=None, labels=None):
         """reference lib/model/SuRSNet.py:131-159."""
@@ -252,11 +272,12 @@ class SuRSNet(nn.Module):
             self.labels_lr = labels
         if not self.can_accelerate(calibs, transforms):
             return self._query_mr_torch(points, calibs, transforms)
-        hr, lr = self._fused(points, calibs)
+        hr, lr = self._fused(points, calibs, transforms)
         self.preds_lr = lr
         self.intermediate_preds_list_lr = [lr]
         self._cached_hr = hr
-        self._q_held = _Held([points, calibs]) if torch.is_tensor(calibs) else None
+        held = [points, calibs] + ([transforms] if transforms is not None else [])
+        self._q_held = _Held(held) if all(torch.is_tensor(t) for t in held) else None
 
     def query_sr(self, points, calibs, transforms=None, labels=None):
         """reference lib/model/SuRSNet.py:161-187 (requires query_mr on the same points first)."""
@@ -266,11 +287,12 @@ class SuRSNet(nn.Module):
             return self._query_sr_torch(points, calibs, transforms)
         # the cached HR result is only valid for the very tensors query_mr saw (object identity while we hold them,
         # unmodified) and the weights / features it ran with (_sync above clears _q_held when either changed)
-        if self._q_held is not None and self._cached_hr is not None and self._q_held.same([points, calibs]):
+        if (self._q_held is not None and self._cached_hr is not None
+                and self._q_held.same([points, calibs] + ([transforms] if transforms is not None else []))):
             hr = self._cached_hr
         else:
             # different points than query_mr saw: the reference would mix them; we recompute both consistently
-            hr, _ = self._fused(points, calibs)
+            hr, _ = self._fused(points, calibs, transforms)
         self.preds_hr = hr
         self.intermediate_preds_list_hr = [hr]
 
@@ -296,7 +318,7 @@ class SuRSNet(nn.Module):
         return feats, in_img[:, None].float()
 
     def _query_mr_torch(self, points, calibs, transforms):
-        self._warn_once("this configuration (multi-view / transforms / perspective / non-default MLP / training)")
+        self._warn_once("this configuration (non-default MLP shapes / --no_residual / training mode / batched subjects)")
         feats, mask = self._local_features(points, calibs, transforms)
         self.point_local_feat = feats
         self.intermediate_preds_list_lr = [mask * self.mlp_lr(f) for f in feats]

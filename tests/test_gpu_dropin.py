@@ -98,6 +98,55 @@ def test_default_precision_meets_the_tolerance_through_the_public_api(case32, go
     helpers.parity_report(lr[0, 0].cpu(), g["pred_lr"], label="public API, default precision, LR")
 
 
+def test_public_api_variants_run_on_the_fused_kernels(case32, golden_dir):
+    """SURVEY §8(f)-4 through the reference's own call shapes: SuRSNet(opt, 'perspective'), opt.num_views = 2 with
+    [V,...] features / calibs / points, and query_mr / query_sr with an image-space `transforms` -- all without the
+    torch fallback (no warning), against the reference goldens / the oracle."""
+    import warnings
+    g = np.load(os.path.join(golden_dir, "variants_golden.npz"))
+    pts = torch.from_numpy(g["points"])[None].to(DEV)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        # perspective
+        opt = helpers.make_opt(loadSize=case32.load_size, z_size=case32.z_size)
+        _, base = make_net(case32, precision=_capi.PREC_FP32)
+        net = SuRSNet(opt, "perspective", precision=_capi.PREC_FP32, encoder=None).to(DEV).eval()
+        net.load_state_dict(base.state_dict())
+        net.im_feat_list_lr, net.im_feat_list_hr = base.im_feat_list_lr, base.im_feat_list_hr
+        calib = torch.from_numpy(g["persp_calib"])[None].to(DEV)
+        net.query_mr(pts, calib)
+        net.query_sr(pts, calib)
+        hr, lr = net.get_preds()
+        assert np.abs(hr[0, 0].cpu().numpy() - g["persp_hr"]).max() < 2e-5 and np.abs(lr[0, 0].cpu().numpy() - g["persp_lr"]).max() < 2e-5
+        # two views of one subject
+        other = syn.SyntheticCase(S=32, seed=int(g["mv_other_seed"]))
+        opt2 = helpers.make_opt(loadSize=case32.load_size, z_size=case32.z_size, num_views=2)
+        net2 = SuRSNet(opt2, precision=_capi.PREC_FP32, encoder=None).to(DEV).eval()
+        net2.load_state_dict(base.state_dict())
+        net2.im_feat_list_lr = [torch.from_numpy(np.stack([case32.feat_lr, other.feat_lr])).to(DEV)]
+        net2.im_feat_list_hr = [torch.from_numpy(np.stack([case32.feat_hr, other.feat_hr])).to(DEV)]
+        p2 = pts.expand(2, -1, -1).contiguous()
+        c2 = torch.from_numpy(g["mv_calibs"]).to(DEV)
+        net2.query_mr(p2, c2)
+        assert net2.preds_lr.shape == (2, 1, pts.shape[2])
+        net2.query_sr(p2, c2)
+        hr, lr = net2.get_preds()
+        assert np.abs(hr[:, 0].cpu().numpy() - g["mv_hr"]).max() < 2e-5 and np.abs(lr[:, 0].cpu().numpy() - g["mv_lr"]).max() < 2e-5
+        # image-space transforms on the single-view net
+        T = torch.tensor([[0.9, 0.05, 0.02], [-0.04, 1.1, -0.03]], device=DEV)
+        calib = torch.from_numpy(case32.calib)[None].to(DEV)
+        base.query_mr(pts, calib, transforms=T)
+        base.query_sr(pts, calib, transforms=T)
+        hr, lr = base.get_preds()
+        ohr, olr = O.query(g["points"], case32.calib, case32.feat_lr, case32.feat_hr, case32.mlp_lr, case32.mlp_hr, load_size=case32.load_size,
+                           uv_transform=T.cpu().numpy())
+        assert np.abs(hr[0, 0].cpu().numpy() - ohr).max() < 2e-5 and np.abs(lr[0, 0].cpu().numpy() - olr).max() < 2e-5
+        # ... and the next plain call is not affected by the transform of the previous one
+        plain = base.query(pts, calib)
+        ohr, _ = O.query(g["points"], case32.calib, case32.feat_lr, case32.feat_hr, case32.mlp_lr, case32.mlp_hr, load_size=case32.load_size)
+        assert np.abs(plain[0, 0].cpu().numpy() - ohr).max() < 2e-5
+
+
 def test_cached_state_is_invalidated_soundly(case32):
     """The library keeps packed weights, repacked features and query_mr's HR result; none of them may go stale:
     weights edited through .data (no version bump), a new feature tensor that reuses a freed tensor's memory,

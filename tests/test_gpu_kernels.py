@@ -589,3 +589,77 @@ def test_error_paths_report_instead_of_falling_back(case32):
             c2.mc_count(torch.zeros((1, 8, 8), device=c2.device), 0.5)
     finally:
         c2.close()
+
+
+def test_perspective_and_image_space_transforms(ctx, case32, golden_dir):
+    """perspective projection (lib/geometry.py:34-48) and the image-space `transforms` of query_mr /
+    query_sr (:27-30) inside every kernel's projection prologue.  Perspective against vectors recorded from the
+    unmodified reference; transforms against the oracle (the reference's own branch cannot run)."""
+    from surs_b200 import _capi
+    g = np.load(os.path.join(golden_dir, "variants_golden.npz"))
+    pts_np = g["points"]
+    pts = torch.from_numpy(pts_np).to(ctx.device)
+    try:
+        ctx.set_projection(True, None)
+        for prec, tol in ((_capi.PREC_FP32, TOL_FP32), (_capi.PREC_DEFAULT, TOL), (_capi.PREC_FP16, TOL_FP16_MAX)):
+            hr, lr = ctx.query(pts, g["persp_calib"], *znum(case32), precision=prec)
+            assert np.abs(hr.cpu().numpy() - g["persp_hr"]).max() < tol and np.abs(lr.cpu().numpy() - g["persp_lr"]).max() < tol
+            assert np.array_equal(hr.cpu().numpy() == 0, g["persp_hr"] == 0)
+        # a perspective grid: generic kernels, equal to explicit points
+        coords, _ = O.create_grid(8, 6, 64, np.array([-0.5] * 3), np.array([0.5] * 3))
+        gp = torch.from_numpy(coords.reshape(3, -1).astype(np.float32)).to(ctx.device)
+        a = ctx.query(gp, g["persp_calib"], *znum(case32), precision=_capi.PREC_FP32)
+        b = ctx.eval_grid((8, 6, 64), [-0.5] * 3, [0.5] * 3, g["persp_calib"], *znum(case32), precision=_capi.PREC_FP32)
+        assert torch.equal(a[0], b[0].reshape(-1)) and torch.equal(a[1], b[1].reshape(-1))
+        # image-space affine on (u, v), orthogonal and perspective
+        T = np.array([[0.9, 0.05, 0.02], [-0.04, 1.1, -0.03]], np.float32)
+        for persp, calib in ((False, case32.calib), (True, g["persp_calib"])):
+            ctx.set_projection(persp, T)
+            ohr, olr = O.query(pts_np, calib, case32.feat_lr, case32.feat_hr, case32.mlp_lr, case32.mlp_hr, load_size=case32.load_size,
+                               perspective=persp, uv_transform=T)
+            for prec, tol in ((_capi.PREC_FP32, TOL_FP32), (_capi.PREC_DEFAULT, TOL)):
+                hr, lr = ctx.query(pts, calib, *znum(case32), precision=prec)
+                assert np.abs(hr.cpu().numpy() - ohr).max() < tol and np.abs(lr.cpu().numpy() - olr).max() < tol
+        # the column-factored dense kernels with an image-space transform (orthogonal): node for node the generic result
+        ctx.set_projection(False, T)
+        coords, _ = O.create_grid(5, 6, 64, np.array([-0.5] * 3), np.array([0.5] * 3))
+        gp = torch.from_numpy(coords.reshape(3, -1).astype(np.float32)).to(ctx.device)
+        ref = ctx.query(gp, case32.calib, *znum(case32), precision=_capi.PREC_FP32)
+        for prec, tol in ((_capi.PREC_FP16X3, TOL_X3_MAX), (_capi.PREC_FP16, TOL_FP16_MAX)):
+            col = ctx.eval_grid((5, 6, 64), [-0.5] * 3, [0.5] * 3, case32.calib, *znum(case32), precision=prec)
+            assert (col[0].reshape(-1) - ref[0]).abs().max().item() < tol and (col[1].reshape(-1) - ref[1]).abs().max().item() < tol
+    finally:
+        ctx.set_projection(False, None)
+    # and the state is really reset
+    hr, _ = ctx.query(pts, case32.calib, *znum(case32), precision=_capi.PREC_FP32)
+    ohr, _ = O.query(pts_np, case32.calib, case32.feat_lr, case32.feat_hr, case32.mlp_lr, case32.mlp_hr, load_size=case32.load_size)
+    assert np.abs(hr.cpu().numpy() - ohr).max() < TOL_FP32
+
+
+def test_multi_view_query(ctx, case32, golden_dir):
+    """opt.num_views = 2 (lib/model/SurfaceClassifier.py:70-76: mean over the views after layer 2) against vectors
+    recorded from the unmodified reference; one and three views against the oracle."""
+    g = np.load(os.path.join(golden_dir, "variants_golden.npz"))
+    other = syn.SyntheticCase(S=32, seed=int(g["mv_other_seed"]))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+    pts = g["points"]
+    ctx.set_features_views(t(np.stack([case32.feat_lr, other.feat_lr])), t(np.stack([case32.feat_hr, other.feat_hr])))
+    hr, lr = ctx.query_views(t(np.stack([pts, pts])), g["mv_calibs"], *znum(case32))
+    assert hr.shape == (2, pts.shape[1])
+    assert np.abs(hr.cpu().numpy() - g["mv_hr"]).max() < TOL_FP32 and np.abs(lr.cpu().numpy() - g["mv_lr"]).max() < TOL_FP32
+    assert np.array_equal(hr.cpu().numpy() == 0, g["mv_hr"] == 0)
+    # three views, ragged point count, different points per view
+    third = syn.SyntheticCase(S=32, seed=9)
+    calibs = np.stack([g["mv_calibs"][0], g["mv_calibs"][1], g["mv_calibs"][0] * np.array([[1], [1], [-1], [1]], np.float32)])
+    p3 = np.stack([syn.random_points(333, seed=s, lo=-0.55, hi=0.55) for s in (1, 2, 3)])
+    fl, fh = [case32.feat_lr, other.feat_lr, third.feat_lr], [case32.feat_hr, other.feat_hr, third.feat_hr]
+    ctx.set_features_views(t(np.stack(fl)), t(np.stack(fh)))
+    hr, lr = ctx.query_views(t(p3), calibs, *znum(case32))
+    ohr, olr = O.query_views(p3, calibs, fl, fh, case32.mlp_lr, case32.mlp_hr, load_size=case32.load_size)
+    assert np.abs(hr.cpu().numpy() - ohr).max() < TOL_FP32 and np.abs(lr.cpu().numpy() - olr).max() < TOL_FP32
+    # one view through the multi-view kernel = the single-view fp32 kernel
+    from surs_b200 import _capi
+    ctx.set_features_views(t(case32.feat_lr[None]), t(case32.feat_hr[None]))
+    hr, lr = ctx.query_views(t(pts[None]), case32.calib[None], *znum(case32))
+    shr, slr = ctx.query(t(pts), case32.calib, *znum(case32), precision=_capi.PREC_FP32)
+    assert (hr[0] - shr).abs().max().item() < 1e-6 and (lr[0] - slr).abs().max().item() < 1e-6

@@ -111,3 +111,21 @@ def test_torch_port_matches_reference(golden_dir, case32):
     assert np.abs(hr - g["pred_hr"]).max() < 1e-5 and np.abs(lr - g["pred_lr"]).max() < 1e-5
     hr2, lr2 = port.query(g["points"], g["calib2"])
     assert np.abs(hr2 - g["pred_hr2"]).max() < 1e-5 and np.abs(lr2 - g["pred_lr2"]).max() < 1e-5
+
+
+def test_oracle_variants_match_reference_goldens(golden_dir):
+    """Perspective projection and two views of one subject (lib/geometry.py:34-48, lib/model/SurfaceClassifier.py:70-76):
+    the oracle's restatement against vectors recorded from the unmodified reference (tests/golden/make_golden_variants.py)."""
+    from surs_b200 import synthetic as syn
+    g = np.load(os.path.join(golden_dir, "variants_golden.npz"))
+    case = syn.SyntheticCase(S=32, seed=0)
+    other = syn.SyntheticCase(S=32, seed=int(g["mv_other_seed"]))
+    pts = g["points"]
+    hr, lr = O.query(pts, g["persp_calib"], case.feat_lr, case.feat_hr, case.mlp_lr, case.mlp_hr, load_size=case.load_size, perspective=True)
+    assert np.abs(hr - g["persp_hr"]).max() < 1e-5 and np.abs(lr - g["persp_lr"]).max() < 1e-5
+    assert np.array_equal(hr == 0, g["persp_hr"] == 0) and (g["persp_hr"] == 0).sum() > 10
+    hr, lr = O.query_views(np.stack([pts, pts]), g["mv_calibs"], [case.feat_lr, other.feat_lr], [case.feat_hr, other.feat_hr],
+                           case.mlp_lr, case.mlp_hr, load_size=case.load_size)
+    assert hr.shape == g["mv_hr"].shape
+    assert np.abs(hr - g["mv_hr"]).max() < 1e-5 and np.abs(lr - g["mv_lr"]).max() < 1e-5
+    assert np.array_equal(hr == 0, g["mv_hr"] == 0)
