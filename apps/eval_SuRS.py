@@ -26,7 +26,8 @@ def main(argv=None):
     cuda = torch.device("cuda:%d" % local)
     torch.cuda.set_device(cuda)
     data = EvalImageFolder(opt)
-    net = SuRSNet(opt, precision={"fp32": _capi.PREC_FP32, "fp16": _capi.PREC_FP16, "fp16x3": _capi.PREC_FP16X3, "fp16r": _capi.PREC_FP16R}[opt.precision]).to(cuda)
+    net = SuRSNet(opt, precision={"fp32": _capi.PREC_FP32, "fp16": _capi.PREC_FP16, "fp16x3": _capi.PREC_FP16X3, "fp16r": _capi.PREC_FP16R}[opt.precision],
+                  encoder_mode=opt.encoder_mode).to(cuda)
     if opt.load_netG_checkpoint_path is not None:
         net.load_state_dict(torch.load(opt.load_netG_checkpoint_path, map_location=cuda))
     net.eval()

@@ -217,6 +217,18 @@ int surs_mc_emit_faces(surs_ctx *ctx, int32_t *faces, const int32_t *seam_in, vo
  * outside bit of the shared plane; the face then holds -1).  0 on every consistent input.  Synchronises. */
 int64_t surs_mc_seam_violations(surs_ctx *ctx);
 
+/* Peer arenas (multi-GPU, one process per GPU on one NVLink / NVSwitch box): `surs_arena_create` allocates `bytes` of
+ * device memory on this context's device and returns its CUDA IPC handle; another process passes the 64 handle bytes to
+ * `surs_arena_open` and gets a pointer that is valid on ITS device and backed by the owner's HBM (peer access over
+ * NVLink).  Every output pointer of surs_mc_emit_verts / surs_mc_emit_faces may point into such a mapping: the
+ * emission then writes each rank's part of the mesh directly at its offset in the gathering rank's buffers -- the gather
+ * of the reference-free multi-GPU path fused into the kernels, no collective for the payload.
+ * `verts` may be NULL in surs_mc_emit_verts when verts_world (with mat) is requested. */
+int surs_arena_create(surs_ctx *ctx, int64_t bytes, void **dev_ptr, unsigned char handle[64]);
+int surs_arena_open(surs_ctx *ctx, const unsigned char handle[64], void **peer_ptr);
+int surs_arena_close(surs_ctx *ctx, void *peer_ptr);
+int surs_arena_destroy(surs_ctx *ctx, void *dev_ptr);
+
 /* float64 -> float32 cast of a volume (what skimage does to its input); n elements. */
 int surs_cast_f64_f32(surs_ctx *ctx, const double *src, float *dst, int64_t n, void *stream);
 

@@ -61,6 +61,10 @@ SIGNATURES = {
     "surs_mc_emit": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "surs_mc_emit_verts": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, ctypes.c_int, _P, _P]),
     "surs_mc_emit_faces": (ctypes.c_int, [_P, _P, _P, _P]),
+    "surs_arena_create": (ctypes.c_int, [_P, _I64, _P, _P]),
+    "surs_arena_open": (ctypes.c_int, [_P, _P, _P]),
+    "surs_arena_close": (ctypes.c_int, [_P, _P]),
+    "surs_arena_destroy": (ctypes.c_int, [_P, _P]),
     "surs_cast_f64_f32": (ctypes.c_int, [_P, _P, _P, _I64, _P]),
     "surs_save_obj_mesh": (ctypes.c_int, [ctypes.c_char_p, _P, _I64, _P, _I64]),
     "surs_selftest_umma": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P]),
@@ -372,23 +376,55 @@ class Context:
         self._mc_vol = vol            # borrowed until the emit calls ran
         return int(nv.value), int(nf.value), int(na.value)
 
-    def mc_emit_verts(self, n_verts, mat=None, vert_id_offset=0, seam_out=None, want_normals=True, plane_offset=0):
+    def mc_emit_verts(self, n_verts, mat=None, vert_id_offset=0, seam_out=None, want_normals=True, plane_offset=0, out_ptrs=None):
+        """out_ptrs = (world, normals, values) raw device addresses (ints; e.g. offsets into a peer arena): the kernel
+        writes there instead of into freshly allocated tensors, no index-space vertices are produced, returns None."""
+        m = None if mat is None else np.ascontiguousarray(np.asarray(mat, dtype=np.float64)[:3, :4])
+        if out_ptrs is not None:
+            world_p, normals_p, values_p = (None if p in (None, 0) else ctypes.c_void_p(int(p)) for p in out_ptrs)
+            with torch.cuda.device(self.device):
+                self._check(self.lib.surs_mc_emit_verts(self._h, None if m is None else m.ctypes.data, None, world_p, normals_p, values_p,
+                                                        int(vert_id_offset), int(plane_offset), _ptr(seam_out), _stream(self.device)))
+            return None
         verts = torch.empty((n_verts, 3), device=self.device, dtype=torch.float32)
         normals = torch.empty((n_verts, 3), device=self.device, dtype=torch.float32) if want_normals else None
         values = torch.empty((n_verts,), device=self.device, dtype=torch.float32) if want_normals else None
         world = torch.empty((n_verts, 3), device=self.device, dtype=torch.float64) if mat is not None else None
-        m = None if mat is None else np.ascontiguousarray(np.asarray(mat, dtype=np.float64)[:3, :4])
         with torch.cuda.device(self.device):
             self._check(self.lib.surs_mc_emit_verts(self._h, None if m is None else m.ctypes.data, _ptr(verts), _ptr(world),
                                                     _ptr(normals), _ptr(values), int(vert_id_offset), int(plane_offset), _ptr(seam_out),
                                                     _stream(self.device)))
         return verts, world, normals, values
 
-    def mc_emit_faces(self, n_faces, seam_in=None):
+    def mc_emit_faces(self, n_faces, seam_in=None, out_ptr=None):
+        if out_ptr is not None:
+            with torch.cuda.device(self.device):
+                self._check(self.lib.surs_mc_emit_faces(self._h, ctypes.c_void_p(int(out_ptr)), _ptr(seam_in), _stream(self.device)))
+            return None
         faces = torch.empty((n_faces, 3), device=self.device, dtype=torch.int32)
         with torch.cuda.device(self.device):
             self._check(self.lib.surs_mc_emit_faces(self._h, _ptr(faces), _ptr(seam_in), _stream(self.device)))
         return faces
+
+    # ---- peer arenas (multi-GPU emission into another rank's memory) ------------------------------
+    def arena_create(self, nbytes):
+        """-> (device address, 64-byte CUDA IPC handle) of `nbytes` of memory on this device."""
+        p, h = _P(), (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.surs_arena_create(self._h, int(nbytes), ctypes.byref(p), h))
+        return int(p.value), bytes(h)
+
+    def arena_open(self, handle):
+        p, h = _P(), (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.surs_arena_open(self._h, h, ctypes.byref(p)))
+        return int(p.value)
+
+    def arena_close(self, peer_ptr):
+        self._check(self.lib.surs_arena_close(self._h, ctypes.c_void_p(int(peer_ptr))))
+
+    def arena_destroy(self, dev_ptr):
+        self._check(self.lib.surs_arena_destroy(self._h, ctypes.c_void_p(int(dev_ptr))))
 
     def marching_cubes(self, vol, level, mat=None):
         """Single-device marching cubes: (verts f32 [V,3], world f64 [V,3] | None, faces i32 [F,3],
@@ -406,6 +442,22 @@ class Context:
             self._check(self.lib.surs_selftest_umma(self._h, _ptr(A), _ptr(B), B.shape[0], A.shape[1], int(bool(tail16)), _ptr(D),
                                                     _stream(self.device)))
         return D
+
+
+class DeviceView:
+    """A typed window into raw device memory (a peer arena) for torch.as_tensor through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr, owner=None):
+        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+        self._owner = owner
+
+
+def tensor_from_ptr(ptr, shape, dtype, device, owner=None):
+    typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1", torch.int64: "<i8"}[dtype]
+    if int(np.prod(shape)) == 0:
+        return torch.empty(tuple(shape), dtype=dtype, device=device)
+    return torch.as_tensor(DeviceView(ptr, shape, typestr, owner), device=device)
 
 
 def save_obj_mesh(mesh_path, verts, faces):

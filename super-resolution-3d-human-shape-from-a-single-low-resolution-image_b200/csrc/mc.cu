@@ -269,7 +269,7 @@ struct McOut {
 __device__ __forceinline__ void write_vertex(const McOut &o, int64_t v, const double pos[3], const double g[3], double value)
 {
     const float fx = (float)pos[0], fy = (float)pos[1], fz = (float)pos[2];
-    o.verts[3 * v] = fx; o.verts[3 * v + 1] = fy; o.verts[3 * v + 2] = fz;
+    if (o.verts) { o.verts[3 * v] = fx; o.verts[3 * v + 1] = fy; o.verts[3 * v + 2] = fz; }
     if (o.verts_world && o.has_mat) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -771,7 +771,7 @@ extern "C" int surs_mc_emit_verts(surs_ctx *ctx, const double *mat, float *verts
     cudaStream_t st = (cudaStream_t)stream;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->mc_vol) SURS_FAIL(ctx, "surs_mc_emit_verts: call surs_mc_count first");
-    if (ctx->mc_nv > 0 && !verts) SURS_FAIL(ctx, "surs_mc_emit_verts: null output");
+    if (ctx->mc_nv > 0 && !verts && !(verts_world && mat)) SURS_FAIL(ctx, "surs_mc_emit_verts: null output (verts, or verts_world with mat)");
     const int64_t nnode = (int64_t)ctx->mc_res[0] * ctx->mc_res[1] * ctx->mc_res[2];
     const int64_t nblocks = (nnode + MC_THREADS - 1) / MC_THREADS;
     if (surs_ensure(ctx, (void **)&ctx->mc_vid, &ctx->mc_vid_cap, sizeof(int32_t) * 3 * (size_t)nnode)) return 1;

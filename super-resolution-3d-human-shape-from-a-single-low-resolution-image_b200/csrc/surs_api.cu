@@ -97,6 +97,54 @@ extern "C" int surs_refine_stats(const surs_ctx *ctx, int64_t *nodes, float *max
 }
 
 // ------------------------------------------------------------------------------------
+// peer arenas: device memory of one rank that the marching-cubes emit kernels of the other ranks write straight into
+// over NVLink (CUDA IPC mapping), i.e. the mesh gather fused into the emission
+// ------------------------------------------------------------------------------------
+extern "C" int surs_arena_create(surs_ctx *ctx, int64_t bytes, void **dev_ptr, unsigned char handle[64])
+{
+    if (!ctx || !dev_ptr || !handle || bytes <= 0) return 1;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    void *p = nullptr;
+    SURS_CUDA(ctx, cudaMalloc(&p, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        SURS_FAIL(ctx, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, 64);
+    *dev_ptr = p;
+    return 0;
+}
+
+extern "C" int surs_arena_open(surs_ctx *ctx, const unsigned char handle[64], void **peer_ptr)
+{
+    if (!ctx || !handle || !peer_ptr) return 1;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    SURS_CUDA(ctx, cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int surs_arena_close(surs_ctx *ctx, void *peer_ptr)
+{
+    if (!ctx) return 1;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    SURS_CUDA(ctx, cudaIpcCloseMemHandle(peer_ptr));
+    return 0;
+}
+
+extern "C" int surs_arena_destroy(surs_ctx *ctx, void *dev_ptr)
+{
+    if (!ctx) return 1;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    SURS_CUDA(ctx, cudaFree(dev_ptr));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
 // parameters
 // ------------------------------------------------------------------------------------
 __global__ void transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols)

@@ -62,8 +62,18 @@ def _checksum(tensors):
 
 
 class SuRSNet(nn.Module):
-    def __init__(self, opt, projection_mode="orthogonal", error_term=None, encoder="auto", precision=_capi.PREC_FP16R):
+    def __init__(self, opt, projection_mode="orthogonal", error_term=None, encoder="auto", precision=_capi.PREC_FP16R,
+                 encoder_mode="eager"):
+        """encoder_mode (built-in encoder only): "eager" = the reference's own execution (fp32 modules, whatever
+        torch.backends.cudnn.allow_tf32 says); "fast" = the same modules with TF32 tensor-core convolutions (PyTorch's
+        default for cuDNN, i.e. what the reference itself gets on a GPU) and the whole super_res + filter_hr + filter_lr
+        forward captured in ONE CUDA graph per input shape (eval mode, CUDA only); "bf16" = "fast" with channels_last
+        + bf16 autocast on top -- measured SLOWER on B200 (31 vs 20 ms at S = 512: layout conversions, GroupNorm and
+        bicubic resampling dominate) and 10x less accurate (feature error 2e-2 vs 2e-3, occupancy up to 0.26 off), kept
+        only so that the measurement can be repeated (scripts/encoder_bench.py)."""
         super().__init__()
+        self.encoder_mode = encoder_mode
+        self._enc_graphs = {}
         self.name = "surs_b200"
         self.opt = opt
         self.num_views = opt.num_views
@@ -140,10 +150,11 @@ class SuRSNet(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         self._w_dirty = True
+        self._enc_graphs = {}                      # captured graphs hold the old parameter storage
         return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, *args, **kwargs):
-        self._w_dirty = True
+        self._w_dirty = True                       # (in-place copies: captured encoder graphs read the new values)
         return super().load_state_dict(*args, **kwargs)
 
     # ------------------------------------------------------------------ encoder side (PyTorch)
@@ -158,12 +169,20 @@ class SuRSNet(nn.Module):
     def super_res(self, images):
         """reference lib/model/SuRSNet.py:124-129."""
         enc = self._need_encoder()
+        if enc is self and self._fast_encoder_ok(images):
+            self.im_SR, self.feature_lr, self.feature_hr = self._encode_fast(images)
+            return self.im_SR, self.feature_lr, self.feature_hr
+        self._fast_out = None
         self.im_SR, self.feature_lr, self.feature_hr = self.super_resolution(images) if enc is self else enc.super_res(images)
         return self.im_SR, self.feature_lr, self.feature_hr
 
     def filter_lr(self, images):
         """reference lib/model/SuRSNet.py:101-110: keeps only the last hourglass output in eval mode."""
         enc = self._need_encoder()
+        fast = getattr(self, "_fast_out", None)
+        if fast is not None and images is self.feature_lr:       # already computed inside the captured graph
+            self.im_feat_list_lr = [fast[0]]
+            return
         self.im_feat_list_lr = self.image_filter_lr(images) if enc is self else enc.filter_lr(images)
         if not self.training:
             self.im_feat_list_lr = [self.im_feat_list_lr[-1]]
@@ -171,9 +190,66 @@ class SuRSNet(nn.Module):
     def filter_hr(self, images):
         """reference lib/model/SuRSNet.py:112-122."""
         enc = self._need_encoder()
+        fast = getattr(self, "_fast_out", None)
+        if fast is not None and images is self.feature_hr:
+            self.im_feat_list_hr = [fast[1]]
+            return
         self.im_feat_list_hr = self.image_filter_hr(images) if enc is self else enc.filter_hr(images)
         if not self.training:
             self.im_feat_list_hr = [self.im_feat_list_hr[-1]]
+
+    # ------------------------------------------------------------------ encoder, B200 configuration
+    def _fast_encoder_ok(self, images):
+        return (self.encoder_mode in ("fast", "bf16") and self._builtin and not self.training and images.is_cuda
+                and not torch.is_grad_enabled())
+
+    def _encoder_forward(self, images):
+        """super_res + filter_hr + filter_lr of lib/train_util.py:57-59 in one function (what the graph captures)."""
+        if self.encoder_mode == "bf16":
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                x = images.contiguous(memory_format=torch.channels_last)
+                im_sr, feature_lr, feature_hr = self.super_resolution(x)
+                f_hr = self.image_filter_hr(feature_hr)[-1]
+                f_lr = self.image_filter_lr(feature_lr)[-1]
+            # the consumers (libsurs repack, reference-style user code) take contiguous NCHW fp32
+            return tuple(t.float().contiguous() for t in (im_sr, feature_lr, feature_hr, f_lr, f_hr))
+        tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = True
+        try:
+            im_sr, feature_lr, feature_hr = self.super_resolution(images)
+            f_hr = self.image_filter_hr(feature_hr)[-1]
+            f_lr = self.image_filter_lr(feature_lr)[-1]
+        finally:
+            torch.backends.cudnn.allow_tf32 = tf32
+        return im_sr, feature_lr, feature_hr, f_lr, f_hr
+
+    def _encode_fast(self, images):
+        key = (tuple(images.shape), images.dtype, images.device.index)
+        entry = self._enc_graphs.get(key)
+        if entry is None:
+            if self.encoder_mode == "bf16" and not getattr(self, "_channels_last_done", False):
+                for mod in (self.super_resolution, self.image_filter_lr, self.image_filter_hr):
+                    mod.to(memory_format=torch.channels_last)
+                self._channels_last_done = True
+            static_in = images.detach().clone()
+            side = torch.cuda.Stream(device=images.device)
+            side.wait_stream(torch.cuda.current_stream(images.device))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(3):                       # warm-up outside the capture (cuDNN plans, autocast caches)
+                    self._encoder_forward(static_in)
+            torch.cuda.current_stream(images.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(graph):
+                static_out = self._encoder_forward(static_in)
+            entry = (graph, static_in, static_out)
+            self._enc_graphs[key] = entry
+        graph, static_in, static_out = entry
+        static_in.copy_(images)
+        graph.replay()
+        # the graph's output buffers are overwritten by the next replay: hand out copies
+        im_sr, feature_lr, feature_hr, f_lr, f_hr = (t.clone() for t in static_out)
+        self._fast_out = (f_lr, f_hr)
+        return im_sr, feature_lr, feature_hr
 
     def filter(self, images):
         """PIFu-style alias: the whole encoder (what gen_mesh does, lib/train_util.py:57-59)."""

@@ -42,6 +42,9 @@ class BaseOptions:
                             "iso-surface can depend on (mesh identical to fp16x3; octree / point queries run fp16x3); "
                             "fp16x3: split operands everywhere (three passes, < 1e-4 from the reference); "
                             "fp32: CUDA-core exact mode; fp16: ONE pass -- explicit opt-in, up to 1.5e-2 from the reference")
+        g.add_argument("--encoder_mode", type=str, default="fast", choices=["eager", "fast", "bf16"],
+                       help="image encoder: fast = TF32 convolutions (PyTorch's GPU default, as the reference) + one CUDA graph "
+                            "per input shape; eager = plain module calls; bf16 = channels_last + bf16 autocast (slower, less accurate)")
         return parser
 
     def parse(self, argv=None):

@@ -8,8 +8,14 @@ exchanges are
   2. the seam: ids of the vertices lying in the plane shared by two slabs travel from the lower
      rank to the upper one (2 x res^2 int32 per mesh), so that the concatenated mesh is
      bit-identical to the single-GPU one (same vertex numbering, no duplicates), and
-  3. the gather of the vertex / face lists to rank 0
-(each of the three once per step for BOTH meshes: the point-to-point operations are batched into one NCCL group).
+  3. the gather of the vertex / face lists on rank 0 -- FUSED INTO THE EMISSION: rank 0 owns two
+     ping-pong device arenas that every other rank maps through CUDA IPC (NVLink peer memory); the
+     marching-cubes emit kernels of rank r write its vertices / faces straight at rank r's offset
+     in rank 0's arrays, followed by one tiny all-reduce as the completion barrier.  No collective
+     carries the payload (SURS_NCCL_GATHER=1 selects the NCCL send / recv gather instead).
+For host results (`reconstruction_from_host`) nothing is gathered on a device at all: every rank
+copies its part over ITS OWN PCIe link into a pinned shared-memory host arena at its offsets and
+rank 0 returns zero-copy numpy views.
 Rank r evaluates planes [lo_r, hi_r + 1) (the halo plane is recomputed, not exchanged) and
 meshes the cells whose lower plane it owns; axis 0 is the outermost scan axis of the marching
 cubes, so concatenation in rank order *is* the single-volume order.
@@ -134,6 +140,134 @@ def pass_up_many(pairs, group=None):
             w.wait()
 
 
+# ---------------------------------------------------------------------------------------------
+# peer arenas (device, owned by rank `dst`) and the pinned shared host arena
+# ---------------------------------------------------------------------------------------------
+def _align(n, a=256):
+    return (int(n) + a - 1) // a * a
+
+
+def mesh_layout(tot_v, tot_f, want_normals=True):
+    """Byte offsets of the eight result arrays (HR then LR: world float64 [V,3], faces int32 [F,3], normals float32
+    [V,3], values float32 [V]) inside an arena, and the total size."""
+    off, lay = 0, []
+    for k in range(2):
+        d = {}
+        for name, nbytes in (("world", 24 * int(tot_v[k])), ("faces", 12 * int(tot_f[k])),
+                             ("normals", 12 * int(tot_v[k]) if want_normals else 0), ("values", 4 * int(tot_v[k]) if want_normals else 0)):
+            d[name] = off
+            off = _align(off + nbytes)
+        lay.append(d)
+    return lay, off
+
+
+def _peer_arenas(ctx, group, need, dst=0):
+    """Two ping-pong device arenas on rank `dst`, mapped into every rank (collective: every rank passes the same need)."""
+    st = getattr(ctx, "_peer_arenas", None)
+    if st is not None and st["capacity"] >= need:
+        return st
+    rank = dist.get_rank(group)
+    if st is not None:
+        for p in st["ptrs"]:
+            (ctx.arena_destroy if st["owner"] else ctx.arena_close)(p)
+    capacity = _align(int(need * 1.5) + (1 << 20), 1 << 20)
+    local, handles = [], [None, None]
+    if rank == dst:
+        local = [ctx.arena_create(capacity) for _ in range(2)]
+        handles = [h for _, h in local]
+    box = [handles]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+    ptrs = [p for p, _ in local] if rank == dst else [ctx.arena_open(h) for h in box[0]]
+    st = {"capacity": capacity, "ptrs": ptrs, "owner": rank == dst, "turn": 0}
+    ctx._peer_arenas = st
+    return st
+
+
+class HostArena:
+    """A POSIX shared-memory segment registered as pinned memory in every rank's process: rank r copies its slice of
+    the result over its own PCIe link, rank 0 reads everything without another copy.  Two halves, used alternately."""
+
+    def __init__(self, ctx, group, need, pin=True):
+        from multiprocessing import shared_memory
+        rank = dist.get_rank(group)
+        self.capacity = _align(int(need * 1.5) + (1 << 20), 1 << 20)
+        box = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=2 * self.capacity)
+            box = [self.shm.name]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=box[0])
+            try:                                      # only the creator unlinks the segment
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.owner = rank == 0
+        self.bytes = torch.frombuffer(self.shm.buf, dtype=torch.uint8, count=2 * self.capacity)
+        self.pinned = bool(pin)
+        if pin:
+            rc = torch.cuda.cudart().cudaHostRegister(self.bytes.data_ptr(), 2 * self.capacity, 0)
+            if int(rc) != 0:
+                raise RuntimeError("cudaHostRegister of the shared host arena failed (%s)" % rc)
+        self.turn = 0
+        dist.barrier(group)
+
+    def half(self):
+        v = self.bytes[self.turn * self.capacity:(self.turn + 1) * self.capacity]
+        self.turn ^= 1
+        return v
+
+    def close(self):
+        if self.pinned:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(self.bytes.data_ptr())
+            except Exception:
+                pass
+        del self.bytes
+        self.shm.close()
+        if self.owner:
+            self.shm.unlink()
+
+
+_ROW_BYTES = {"world": 24, "faces": 12, "normals": 12, "values": 4}
+
+
+def fill_host_arena(half, layout, emitted, offs, rank):
+    """This rank's slices of the eight result arrays -> their place in the arena half (asynchronous for CUDA sources and
+    a pinned arena).  emitted: per mesh (world, faces, normals, values); offs: exclusive row offsets [world, 4]."""
+    for k, e in enumerate(emitted):
+        for name, t, off_rows in (("world", e[0], offs[rank, 2 * k]), ("faces", e[1], offs[rank, 2 * k + 1]),
+                                  ("normals", e[2], offs[rank, 2 * k]), ("values", e[3], offs[rank, 2 * k])):
+            if t is None or t.numel() == 0:
+                continue
+            start = layout[k][name] + _ROW_BYTES[name] * int(off_rows)
+            half[start:start + t.numel() * t.element_size()].view(t.dtype).view(t.shape).copy_(t, non_blocking=True)
+
+
+def read_host_arena(half, layout, tot_v, tot_f):
+    """Zero-copy numpy views of the eight arrays (the reference's 8-tuple order)."""
+    out, buf = [], half.numpy()
+    for k in range(2):
+        L, nv, nf = layout[k], int(tot_v[k]), int(tot_f[k])
+        out += [buf[L["world"]:L["world"] + 24 * nv].view(np.float64).reshape(nv, 3),
+                buf[L["faces"]:L["faces"] + 12 * nf].view(np.int32).reshape(nf, 3),
+                buf[L["normals"]:L["normals"] + 12 * nv].view(np.float32).reshape(nv, 3),
+                buf[L["values"]:L["values"] + 4 * nv].view(np.float32).reshape(nv)]
+    return tuple(out)
+
+
+def _host_arena(ctx, group, need):
+    st = getattr(ctx, "_host_arena", None)
+    if st is not None and st.capacity >= need:
+        return st
+    if st is not None:
+        st.close()
+    st = HostArena(ctx, group, need)
+    ctx._host_arena = st
+    return st
+
+
 def _mc_contexts(ctx):
     """Marching-cubes state lives in the context between count and emit; a sibling context on the same device
     lets the HR and the LR volume go through count -> exchange -> emit together (one exchange round for both)."""
@@ -188,22 +322,70 @@ def reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, transform
     allc = allc.cpu().numpy()
     offs = exclusive_offsets(allc)
     tick("all-gather of the counts")
+    # gather == True: emit straight into rank 0's arena through the NVLink peer mapping (no payload collective)
+    fused = gather is True and os.environ.get("SURS_NCCL_GATHER") is None
+    layout = base = None
+    if fused:
+        tot_v, tot_f = allc[:, [0, 2]].sum(0), allc[:, [1, 3]].sum(0)
+        layout, need = mesh_layout(tot_v, tot_f, want_normals)
+        arenas = _peer_arenas(ctx, group, need)
+        base = arenas["ptrs"][arenas["turn"]]
+        arenas["turn"] ^= 1
     emitted, seams = [], []
     for k, c in enumerate(ctxs):
         seam_out = torch.empty((2, R1, R2), device=dev, dtype=torch.int32) if rank + 1 < world else None
         seam_in = torch.empty((2, R1, R2), device=dev, dtype=torch.int32) if rank > 0 else None
-        _, world_v, normals, values = c.mc_emit_verts(counts[k][0], mat, vert_id_offset=int(offs[rank, 2 * k]), seam_out=seam_out,
-                                                      want_normals=want_normals, plane_offset=lo)
-        emitted.append([world_v, None, normals, values])
+        ov = int(offs[rank, 2 * k])
+        if fused:
+            L = layout[k]
+            c.mc_emit_verts(counts[k][0], mat, vert_id_offset=ov, seam_out=seam_out, plane_offset=lo,
+                            out_ptrs=(base + L["world"] + 24 * ov, (base + L["normals"] + 12 * ov) if want_normals else None,
+                                      (base + L["values"] + 4 * ov) if want_normals else None))
+            emitted.append(None)
+        else:
+            _, world_v, normals, values = c.mc_emit_verts(counts[k][0], mat, vert_id_offset=ov, seam_out=seam_out,
+                                                          want_normals=want_normals, plane_offset=lo)
+            emitted.append([world_v, None, normals, values])
         seams.append((seam_out, seam_in))
     tick("emit vertices x2")
     pass_up_many(seams, group)
     tick("seam hand-over")
     for k, c in enumerate(ctxs):
-        emitted[k][1] = c.mc_emit_faces(counts[k][1], seam_in=seams[k][1])
+        if fused:
+            c.mc_emit_faces(counts[k][1], seam_in=seams[k][1], out_ptr=base + layout[k]["faces"] + 12 * int(offs[rank, 2 * k + 1]))
+        else:
+            emitted[k][1] = c.mc_emit_faces(counts[k][1], seam_in=seams[k][1])
     tick("emit faces x2")
+    if gather == "local":
+        return tuple(tuple(e) for e in emitted), allc, offs
     if not gather:
         return tuple(tuple(e) for e in emitted)
+
+    def check_seams():
+        if rank > 0:
+            # the lower slab owns the vertices of the shared plane; a missing id means the two ranks disagree about an
+            # inside / outside bit there (cannot happen while both evaluate the plane with the same arithmetic)
+            bad = sum(c.mc_seam_violations() for c in ctxs)
+            if bad:
+                raise RuntimeError("slab seam mismatch on rank %d: %d face corners reference a vertex the lower slab does not have" % (rank, bad))
+
+    if fused:
+        # completion barrier: stream-ordered behind every rank's emit kernels; when it has run on rank 0 all peer
+        # writes have landed in its arena
+        flag = torch.zeros(1, device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, group=group)
+        tick("completion all-reduce")
+        check_seams()
+        if rank != 0:
+            return (None, None)
+        results = []
+        for k in range(2):
+            L, nv, nf = layout[k], int(tot_v[k]), int(tot_f[k])
+            results.append((_capi.tensor_from_ptr(base + L["world"], (nv, 3), torch.float64, dev),
+                            _capi.tensor_from_ptr(base + L["faces"], (nf, 3), torch.int32, dev),
+                            _capi.tensor_from_ptr(base + L["normals"], (nv, 3), torch.float32, dev) if want_normals else None,
+                            _capi.tensor_from_ptr(base + L["values"], (nv,), torch.float32, dev) if want_normals else None))
+        return tuple(results)
     items = []
     for k, e in enumerate(emitted):
         items += [(e[0], allc[:, 2 * k]), (e[1], allc[:, 2 * k + 1])]
@@ -211,12 +393,7 @@ def reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, transform
             items += [(e[2], allc[:, 2 * k]), (e[3], allc[:, 2 * k])]
     got = gather_rows_many(items, 0, group)
     tick("gather of the mesh lists")
-    if rank > 0:
-        # the lower slab owns the vertices of the shared plane; a missing id means the two ranks disagree about an
-        # inside / outside bit there (cannot happen while both evaluate the plane with the same arithmetic)
-        bad = sum(c.mc_seam_violations() for c in ctxs)
-        if bad:
-            raise RuntimeError("slab seam mismatch on rank %d: %d face corners reference a vertex the lower slab does not have" % (rank, bad))
+    check_seams()
     if rank != 0:
         return (None, None)
     per = 4 if want_normals else 2
@@ -232,7 +409,9 @@ def reconstruction_from_host(ctx, feat_lr_host, feat_hr_host, res, b_min, b_max,
     """The host-facing multi-GPU call: every rank uploads the two encoder feature maps (NCHW fp32 host tensors,
     ideally pinned) to its GPU, reconstructs its slab, and rank 0 returns the reference's 8-tuple
     (lib/mesh_util.py:8-49: verts float64 world coordinates, faces int32, normals, values -- HR then LR) as host
-    numpy arrays; the other ranks return None."""
+    numpy arrays; the other ranks return None.  With several ranks the arrays are zero-copy views of a pinned
+    shared-memory arena that every rank filled over its own PCIe link; they stay valid until the call after next
+    (two halves, used alternately).  SURS_NCCL_GATHER=1: gather on rank 0's device and copy from there instead."""
     from .lib.mesh_util import _to_host
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     rank = dist.get_rank(group) if distributed else 0
@@ -241,7 +420,22 @@ def reconstruction_from_host(ctx, feat_lr_host, feat_hr_host, res, b_min, b_max,
     lo, hi = slab_ranges(int(res[0]), world)[rank]
     hi = min(hi + 1, int(res[0]))
     ctx.set_features_host(feat_lr_host, feat_hr_host, u_range=slab_u_range(res, b_min, b_max, calib, lo, hi))
-    hr, lr = reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, precision=precision, group=group)
-    if hr is None:
+    if not distributed or os.environ.get("SURS_NCCL_GATHER") is not None:
+        hr, lr = reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, precision=precision, group=group)
+        if hr is None:
+            return None
+        return tuple(_to_host(list(hr) + list(lr)))
+    emitted, allc, offs = reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, precision=precision, group=group, gather="local")
+    tot_v, tot_f = allc[:, [0, 2]].sum(0), allc[:, [1, 3]].sum(0)
+    layout, need = mesh_layout(tot_v, tot_f, True)
+    arena = _host_arena(ctx, group, need)
+    half = arena.half()
+    fill_host_arena(half, layout, emitted, offs, rank)
+    torch.cuda.current_stream(ctx.device).synchronize()
+    bad = sum(c.mc_seam_violations() for c in _mc_contexts(ctx)) if rank > 0 else 0
+    if bad:
+        raise RuntimeError("slab seam mismatch on rank %d: %d face corners reference a vertex the lower slab does not have" % (rank, bad))
+    dist.barrier(group)                                   # every rank's copies have landed in the host arena
+    if rank != 0:
         return None
-    return tuple(_to_host(list(hr) + list(lr)))
+    return read_host_arena(half, layout, tot_v, tot_f)

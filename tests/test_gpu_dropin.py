@@ -330,6 +330,51 @@ def test_gen_mesh_with_builtin_encoder(tmp_path):
         assert lines[0].startswith("v ") and lines[-1].startswith("f ") and len(lines) > 100
 
 
+def test_fast_encoder_mode_matches_eager(tmp_path):
+    """encoder_mode='fast' (TF32 convolutions + ONE CUDA graph of super_res + filter_hr + filter_lr) produces the eager
+    modules' feature maps up to TF32 rounding (2e-3 relative, the reference's own GPU numerics), replays correctly for
+    new images and after a weight update."""
+    import types
+    opt = types.SimpleNamespace(**vars(helpers.make_opt(loadSize=64, resolution=64)), num_stack_lr=3, num_stack_hr=1, hg_depth=2, hg_dim=256,
+                                norm="group", n_block=[2, 2, 2], rgb_range=255, scale=2, residual=True)
+    torch.manual_seed(0)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                   # the eager side in true fp32
+    eager = SuRSNet(opt, encoder_mode="eager").to(DEV).eval()
+    for m in eager.modules():
+        if isinstance(m, torch.nn.Conv2d) and m.weight.shape[1] > 3:
+            torch.nn.init.kaiming_normal_(m.weight, a=0.2)
+    fast = SuRSNet(opt, encoder_mode="fast").to(DEV).eval()
+    fast.load_state_dict(eager.state_dict())
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    with torch.no_grad():
+        for seed in (1, 2, 1):
+            img = torch.randn(1, 3, 32, 32, generator=torch.Generator().manual_seed(seed)).to(DEV)
+            for n in (eager, fast):
+                _, flr, fhr = n.super_res(img)
+                n.filter_hr(fhr)
+                n.filter_lr(flr)
+            e_lr, e_hr = rel(fast.im_feat_list_lr[-1], eager.im_feat_list_lr[-1]), rel(fast.im_feat_list_hr[0], eager.im_feat_list_hr[0])
+            print("fast encoder vs eager: relative L2 error lr %.3g hr %.3g" % (e_lr, e_hr))
+            assert e_lr < 5e-3 and e_hr < 5e-3
+            assert fast.im_feat_list_lr[-1].dtype == torch.float32 and fast.im_feat_list_lr[-1].is_contiguous()
+        assert len(fast._enc_graphs) == 1                      # one capture, replayed
+        # a weight update is seen by the captured graph (in-place load_state_dict)
+        sd = {k: v.clone() for k, v in eager.state_dict().items()}
+        sd["image_filter_hr.conv5.bias"] += 1.0
+        eager.load_state_dict(sd)
+        fast.load_state_dict(sd)
+        for n in (eager, fast):
+            _, flr, fhr = n.super_res(img)
+            n.filter_hr(fhr)
+        assert rel(fast.im_feat_list_hr[0], eager.im_feat_list_hr[0]) < 5e-3
+        # a different feature tensor than the one super_res returned goes through the eager filter
+        other = fhr.clone()
+        fast.filter_hr(other)
+        assert rel(fast.im_feat_list_hr[0], eager.image_filter_hr(other)[-1]) < 5e-3
+    torch.backends.cudnn.allow_tf32 = tf32
+
+
 def test_eval_cli_end_to_end(tmp_path):
     """apps/eval_SuRS.py: image folder + checkpoint file -> OBJ files (reference flags)."""
     import importlib.util

@@ -39,6 +39,25 @@ def _worker(rank, world, port, res, out, refined=False):
         prec = _capi.PREC_FP16R if refined else _capi.PREC_FP16
         got = parallel.reconstruct_slab(ctx, (res,) * 3, bmin, bmax, case.calib, zn, zd, mat, precision=prec)
         ok = True
+        # the three exchange paths give the same mesh: emission fused with the gather through the NVLink peer arena
+        # (default, twice: the arenas ping-pong), the NCCL send / recv gather, and the pinned shared host arena
+        got2 = parallel.reconstruct_slab(ctx, (res,) * 3, bmin, bmax, case.calib, zn, zd, mat, precision=prec)
+        os.environ["SURS_NCCL_GATHER"] = "1"
+        got_nccl = parallel.reconstruct_slab(ctx, (res,) * 3, bmin, bmax, case.calib, zn, zd, mat, precision=prec)
+        del os.environ["SURS_NCCL_GATHER"]
+        f_lr_h, f_hr_h = torch.from_numpy(case.feat_lr).pin_memory(), torch.from_numpy(case.feat_hr).pin_memory()
+        host = parallel.reconstruction_from_host(ctx, f_lr_h, f_hr_h, (res,) * 3, bmin, bmax, case.calib, zn, zd, mat, precision=prec)
+        host2 = parallel.reconstruction_from_host(ctx, f_lr_h, f_hr_h, (res,) * 3, bmin, bmax, case.calib, zn, zd, mat, precision=prec)
+        ctx.set_features(t(case.feat_lr), t(case.feat_hr))               # whole maps again for the single-GPU check below
+        if rank == 0:
+            flat = lambda g: [x for mesh in g for x in mesh]
+            for other in (got2, got_nccl):
+                ok = ok and all(torch.equal(a, b) for a, b in zip(flat(got), flat(other)))
+            for h in (host, host2):
+                ok = ok and all(np.array_equal(a.cpu().numpy(), b) for a, b in zip(flat(got), h))
+            print("rank0: fused / NCCL / host-arena paths identical:", ok, flush=True)
+        else:
+            ok = got == (None, None) and host is None
         if rank == 0:
             vols = ctx.eval_grid((res,) * 3, bmin, bmax, case.calib, zn, zd, precision=prec)
             for (w, f, n, v), vol in zip(got, vols):

@@ -93,3 +93,64 @@ def test_gather_and_seam_exchange_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_mesh_layout_is_aligned_and_disjoint():
+    lay, total = parallel.mesh_layout([1000, 7], [1999, 11])
+    spans = []
+    for k, (nv, nf) in enumerate(((1000, 1999), (7, 11))):
+        for name, n in (("world", 24 * nv), ("faces", 12 * nf), ("normals", 12 * nv), ("values", 4 * nv)):
+            assert lay[k][name] % 256 == 0
+            spans.append((lay[k][name], lay[k][name] + n))
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= total
+
+
+def _arena_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank holds its rows of the two meshes; the shared host arena receives them at the global offsets
+        nv = np.array([[3, 2], [0, 4], [5, 1]][:world])           # [rank][mesh] vertices
+        nf = 2 * nv + 1
+        allc = np.stack([nv[:, 0], nf[:, 0], nv[:, 1], nf[:, 1]], 1)
+        offs = parallel.exclusive_offsets(allc)
+        tot_v, tot_f = allc[:, [0, 2]].sum(0), allc[:, [1, 3]].sum(0)
+        layout, need = parallel.mesh_layout(tot_v, tot_f)
+        arena = parallel.HostArena(None, None, need, pin=False)
+        mk = lambda n, cols, dt, tag: (torch.arange(n * cols, dtype=torch.float64).reshape((n, cols) if cols > 1 else (n,)) + 1000 * rank + tag).to(dt)
+        for rep in range(3):                                       # the two halves alternate
+            emitted = [(mk(nv[rank, k], 3, torch.float64, 10 * k + rep), mk(nf[rank, k], 3, torch.int32, 20 * k), mk(nv[rank, k], 3, torch.float32, 30 * k),
+                        mk(nv[rank, k], 1, torch.float32, 40 * k)) for k in range(2)]
+            half = arena.half()
+            parallel.fill_host_arena(half, layout, emitted, offs, rank)
+            dist.barrier()
+            ok = True
+            if rank == 0:
+                got = parallel.read_host_arena(half, layout, tot_v, tot_f)
+                for k in range(2):
+                    for j, (cols, dt, tag, cnt) in enumerate(((3, torch.float64, 10 * k + rep, nv), (3, torch.int32, 20 * k, nf), (3, torch.float32, 30 * k, nv),
+                                                              (1, torch.float32, 40 * k, nv))):
+                        want = torch.cat([(torch.arange(cnt[r, k] * cols, dtype=torch.float64).reshape((cnt[r, k], cols) if cols > 1 else (cnt[r, k],))
+                                           + 1000 * r + tag).to(dt) for r in range(world)]).numpy()
+                        ok = ok and np.array_equal(got[4 * k + j], want)
+            dist.barrier()
+            out.put((rank, ok))
+        arena.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shared_host_arena_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_arena_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(3 * world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
