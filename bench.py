@@ -580,7 +580,8 @@ def run_ours(args):
             e2e = {"value": n_queries / dt, "unit": "queries/s",
                    "h2d_bytes_per_step": int(up.item()),
                    "d2h_bytes_per_step": sum(int(a.nbytes) for a in r), "s_per_mesh": dt,
-                   "note": "every rank uploads the stripe of the two feature maps its slab samples (h2d = sum over ranks); meshes gathered over NCCL, host copy on rank 0",
+                   "note": "every rank uploads the stripe of the two feature maps its slab samples (h2d = sum over ranks) and copies its part of the "
+                           "meshes over its own PCIe link into a pinned shared-memory host arena (d2h = sum over ranks); rank 0 returns zero-copy views",
                    "verts_hr": int(r[0].shape[0]), "faces_hr": int(r[1].shape[0]), "verts_lr": int(r[4].shape[0]), "faces_lr": int(r[5].shape[0]),
                    "mesh_sha256": mesh_sha256([r[0], r[1], r[4], r[5]])}
 

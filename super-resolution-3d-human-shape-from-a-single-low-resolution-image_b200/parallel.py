@@ -224,10 +224,19 @@ class HostArena:
                 torch.cuda.cudart().cudaHostUnregister(self.bytes.data_ptr())
             except Exception:
                 pass
+        if getattr(self, "closed", False):
+            return
+        self.closed = True
         del self.bytes
-        self.shm.close()
+        try:
+            self.shm.close()
+        except BufferError:                                # numpy views handed to the caller are still alive
+            pass
         if self.owner:
-            self.shm.unlink()
+            try:
+                self.shm.unlink()
+            except FileNotFoundError:
+                pass
 
 
 _ROW_BYTES = {"world": 24, "faces": 12, "normals": 12, "values": 4}
@@ -258,6 +267,7 @@ def read_host_arena(half, layout, tot_v, tot_f):
 
 
 def _host_arena(ctx, group, need):
+    import atexit
     st = getattr(ctx, "_host_arena", None)
     if st is not None and st.capacity >= need:
         return st
@@ -265,6 +275,7 @@ def _host_arena(ctx, group, need):
         st.close()
     st = HostArena(ctx, group, need)
     ctx._host_arena = st
+    atexit.register(st.close)                          # unlink the shared-memory segment when the process ends
     return st
 
 
