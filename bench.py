@@ -429,11 +429,9 @@ def run_ours(args):
             def run():
                 a, b, n_eval = ctx.eval_grid_octree((r, r, r), b_min, b_max, case.calib, zn, zd, 0.05, precision=prec)
                 st = ctx.octree_stats()
-                va, vb = ctx.cast_f64_f32(a), ctx.cast_f64_f32(b)
-                del a, b
                 m = bsdf.grid_matrix(r, b_min, b_max)[:3, :4]
                 counts = []
-                for vol in (va, vb):
+                for vol in (a, b):                                  # float64 volumes: cast inside the marching-cubes bit pass
                     nv, nf, _ = ctx.mc_count(vol, 0.5)
                     ctx.mc_emit_verts(nv, m)
                     ctx.mc_emit_faces(nf)

@@ -206,6 +206,14 @@ int surs_octree_cells(surs_ctx *ctx, const int res[3], int reso, double threshol
 enum { SURS_MC_LOWER_FOREIGN = 1 };
 int surs_mc_count(surs_ctx *ctx, const float *vol, const int res[3], float level, int flags,
                   int64_t *n_verts, int64_t *n_faces, int64_t *n_ambiguous, void *stream);
+/* surs_mc_count_f64: the same for a float64 volume (lib/sdf.py keeps the octree volumes in float64; skimage casts its
+ * input to float32): the pass that takes the inside / outside bits also writes the float32 copy into vol32 [dev, caller
+ * allocated, borrowed until the emit calls ran] -- no separate cast pass.
+ * surs_mc_value_range: minimum and maximum of the last counted volume, a by-product of that same pass; it is what
+ * skimage compares the level with ("Surface level must be within volume data range") -- no separate reduction pass. */
+int surs_mc_count_f64(surs_ctx *ctx, const double *vol64, float *vol32, const int res[3], float level, int flags,
+                      int64_t *n_verts, int64_t *n_faces, int64_t *n_ambiguous, void *stream);
+int surs_mc_value_range(surs_ctx *ctx, float *vmin, float *vmax);
 int surs_mc_interior_stats(surs_ctx *ctx, int64_t *n_interior_ambiguous, int64_t *n_tunnels);
 int surs_mc_emit(surs_ctx *ctx, const double *mat, float *verts, double *verts_world,
                  int32_t *faces, float *normals, float *values, void *stream);

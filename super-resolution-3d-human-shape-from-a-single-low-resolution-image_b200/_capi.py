@@ -58,6 +58,8 @@ SIGNATURES = {
     "surs_octree_cells": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_double, _P, _P, _P, _P]),
     "surs_mc_count": (ctypes.c_int, [_P, _P, _P, ctypes.c_float, ctypes.c_int, _P, _P, _P, _P]),
     "surs_mc_interior_stats": (ctypes.c_int, [_P, _P, _P]),
+    "surs_mc_count_f64": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_float, ctypes.c_int, _P, _P, _P, _P]),
+    "surs_mc_value_range": (ctypes.c_int, [_P, _P, _P]),
     "surs_mc_emit": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "surs_mc_emit_verts": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, ctypes.c_int, _P, _P]),
     "surs_mc_emit_faces": (ctypes.c_int, [_P, _P, _P, _P]),
@@ -366,15 +368,28 @@ class Context:
 
     # ---- marching cubes ---------------------------------------------------------------
     def mc_count(self, vol, level, flags=0):
-        """vol: fp32 contiguous device volume.  Returns (n_verts, n_faces, n_ambiguous_cells)."""
-        assert vol.dtype == torch.float32 and vol.is_contiguous() and vol.device == self.device
+        """vol: contiguous device volume, fp32 -- or float64 (octree volumes): the float32 copy skimage would make is
+        then written by the same pass and kept as ``self._mc_vol``.  Returns (n_verts, n_faces, n_ambiguous_cells);
+        ``mc_value_range()`` gives the volume's (min, max) afterwards."""
+        assert vol.dtype in (torch.float32, torch.float64) and vol.is_contiguous() and vol.device == self.device
         r = (ctypes.c_int * 3)(*[int(v) for v in vol.shape])
         nv, nf, na = _I64(0), _I64(0), _I64(0)
         with torch.cuda.device(self.device):
-            self._check(self.lib.surs_mc_count(self._h, _ptr(vol), r, float(level), int(flags), ctypes.byref(nv), ctypes.byref(nf),
-                                               ctypes.byref(na), _stream(self.device)))
+            if vol.dtype == torch.float64:
+                vol32 = torch.empty(vol.shape, device=self.device, dtype=torch.float32)
+                self._check(self.lib.surs_mc_count_f64(self._h, _ptr(vol), _ptr(vol32), r, float(level), int(flags), ctypes.byref(nv),
+                                                       ctypes.byref(nf), ctypes.byref(na), _stream(self.device)))
+                vol = vol32
+            else:
+                self._check(self.lib.surs_mc_count(self._h, _ptr(vol), r, float(level), int(flags), ctypes.byref(nv), ctypes.byref(nf),
+                                                   ctypes.byref(na), _stream(self.device)))
         self._mc_vol = vol            # borrowed until the emit calls ran
         return int(nv.value), int(nf.value), int(na.value)
+
+    def mc_value_range(self):
+        lo, hi = ctypes.c_float(0), ctypes.c_float(0)
+        self._check(self.lib.surs_mc_value_range(self._h, ctypes.byref(lo), ctypes.byref(hi)))
+        return float(lo.value), float(hi.value)
 
     def mc_emit_verts(self, n_verts, mat=None, vert_id_offset=0, seam_out=None, want_normals=True, plane_offset=0, out_ptrs=None):
         """out_ptrs = (world, normals, values) raw device addresses (ints; e.g. offsets into a peer arena): the kernel

@@ -219,6 +219,9 @@ struct surs_ctx {
     int64_t mc_nv, mc_nf, mc_id_offset;
     int mc_fast;                           // R2 % 4 == 0: quad classification + compact active-cell list
     int64_t mc_nact;
+    float mc_vmin, mc_vmax;                // value range of the last counted volume (surs_mc_value_range)
+    unsigned mc_range_host[2];
+    int64_t mc_cap_hint;                   // active cells of the previous volume: estimate of the next list length
     void *mc_cells;                        // active cells in scan order (CellRec, mc.cu)
     size_t mc_cells_cap;
     void *mc_block_tot;                    // per-block totals, then exclusive prefix (uint2 / uint4)

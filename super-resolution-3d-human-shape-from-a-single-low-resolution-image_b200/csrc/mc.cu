@@ -450,24 +450,52 @@ __global__ void mc_seam_export_kernel(McParams p, const int32_t *__restrict__ vi
 //                       ambiguity deciders -> vertex / triangle counts, block-relative offsets
 //   mc_list_verts / mc_list_faces   one thread per active cell
 // ------------------------------------------------------------------------------------------
-struct CellRec { uint32_t lin, vbase, fbase, pad; };     // vbase / fbase relative to the cell's mc_cell_kernel block
+// vbase / fbase relative to the cell's mc_cell_kernel block; cls = table entry | owned vertex slots << 16: the list
+// kernels do not repeat the classification (deciders, interior test), and the face kernel does not touch the volume
+struct CellRec { uint32_t lin, vbase, fbase, cls; };
 
 constexpr int MC_SIGN_WARPS = 8;
 
-__global__ void __launch_bounds__(MC_SIGN_WARPS * 32) mc_sign_kernel(const float *__restrict__ vol, float level, int64_t nrows, int R2, int W,
-                                                                      uint32_t *__restrict__ bits)
+// float <-> unsigned key with the same ordering (for atomicMin / atomicMax on the value range)
+__device__ __forceinline__ unsigned f2key(float f)
+{
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float key2f(unsigned k)
+{
+    const unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    float f;
+    memcpy(&f, &b, sizeof(f));
+    return f;
+}
+
+// One pass over the volume does everything that needs every value: the inside / outside bit per node, the value range
+// (what skimage checks the level against: replaces a separate aminmax pass) and, for a float64 source (octree volumes,
+// lib/sdf.py keeps them in float64), the float32 copy that skimage makes of its input (replaces a separate cast pass).
+// range[0] / range[1]: ordered keys of the minimum / maximum, updated with one guarded atomic per warp.
+template <typename T, bool COPY32>
+__global__ void __launch_bounds__(MC_SIGN_WARPS * 32) mc_sign_kernel(const T *__restrict__ vol, float *__restrict__ vol32, float level, int64_t nrows,
+                                                                      int R2, int W, uint32_t *__restrict__ bits, unsigned *__restrict__ range)
 {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * MC_SIGN_WARPS + (threadIdx.x >> 5);
     if (row >= nrows) return;
-    const float *src = vol + row * R2;
+    const T *src = vol + row * R2;
     uint32_t *dst = bits + row * W;
+    float lo = INFINITY, hi = -INFINITY;
     for (int w0 = 0; w0 < W; w0 += 16) {
         float v[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
             const int k = (w0 + u) * 32 + lane;
-            v[u] = (w0 + u < W && k < R2) ? __ldcs(src + k) : level;      // streamed: nothing re-reads the floats from L1
+            const bool ok = w0 + u < W && k < R2;
+            v[u] = ok ? (float)__ldcs(src + k) : level;                  // streamed: nothing re-reads the source from L1
+            if (ok) {
+                lo = fminf(lo, v[u]);
+                hi = fmaxf(hi, v[u]);
+                if (COPY32) vol32[row * R2 + k] = v[u];
+            }
         }
         uint32_t mine = 0;
 #pragma unroll
@@ -476,6 +504,39 @@ __global__ void __launch_bounds__(MC_SIGN_WARPS * 32) mc_sign_kernel(const float
             if (lane == u) mine = word;
         }
         if (lane < 16 && w0 + lane < W) dst[w0 + lane] = mine;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {                                                     // after the first rows the guards almost never pass
+        const unsigned klo = f2key(lo), khi = f2key(hi);
+        if (klo < __ldcg(range)) atomicMin(range, klo);
+        if (khi > __ldcg(range + 1)) atomicMax(range + 1, khi);
+    }
+}
+
+// general path (any shape): value range (+ float32 copy) as a grid-stride pass
+template <typename T, bool COPY32>
+__global__ void mc_range_kernel(const T *__restrict__ vol, float *__restrict__ vol32, int64_t n, unsigned *__restrict__ range)
+{
+    float lo = INFINITY, hi = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = (float)vol[i];
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+        if (COPY32) vol32[i] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned klo = f2key(lo), khi = f2key(hi);
+        if (klo < __ldcg(range)) atomicMin(range, klo);
+        if (khi > __ldcg(range + 1)) atomicMax(range + 1, khi);
     }
 }
 
@@ -502,10 +563,14 @@ __device__ __forceinline__ void block_scan1(unsigned a, unsigned &excl, unsigned
     __syncthreads();
 }
 
+// WRITE pass: `totals` (device) holds the number of active cells; nothing is written when it exceeds `cap` (the host
+// then repeats the pass with a larger list -- the first launch runs on an estimate so that no synchronisation is needed
+// between counting and compaction)
 template <bool WRITE>
 __global__ void __launch_bounds__(MC_THREADS) mc_bits_kernel(McParams p, const uint32_t *__restrict__ bits, int W, uint32_t nthreads,
-                                                             uint4 *block_tot, CellRec *cells)
+                                                             uint4 *block_tot, CellRec *cells, const unsigned long long *totals, uint32_t cap)
 {
+    if (WRITE && *totals > (unsigned long long)cap) return;
     const uint32_t t = blockIdx.x * MC_THREADS + threadIdx.x;
     uint32_t act = 0, row = 0;
     int w = 0;
@@ -541,8 +606,16 @@ __global__ void __launch_bounds__(MC_THREADS) mc_bits_kernel(McParams p, const u
     }
 }
 
-__global__ void __launch_bounds__(MC_THREADS) mc_cell_kernel(McParams p, CellRec *cells, uint32_t nact, uint4 *block_tot, unsigned long long *n_amb)
+__global__ void __launch_bounds__(MC_THREADS) mc_cell_kernel(McParams p, CellRec *cells, const unsigned long long *nact_dev, uint32_t cap, uint4 *block_tot,
+                                                             unsigned long long *n_amb)
 {
+    const unsigned long long nact_ll = *nact_dev;
+    if (nact_ll > (unsigned long long)cap) return;
+    const uint32_t nact = (uint32_t)nact_ll;
+    if (blockIdx.x * MC_THREADS >= nact) {                      // launched for the capacity: blocks beyond the list only zero their total
+        if (threadIdx.x == 0) block_tot[blockIdx.x] = make_uint4(0, 0, 0, 0);
+        return;
+    }
     const uint32_t a = blockIdx.x * MC_THREADS + threadIdx.x;
     Cell c;
     c.nv = 0; c.nt = 0; c.ambiguous = 0; c.interior = 0;
@@ -553,7 +626,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_cell_kernel(McParams p, CellRec
     }
     unsigned ev, ef, tv, tf;
     block_scan2((unsigned)c.nv, (unsigned)c.nt, ev, ef, tv, tf);
-    if (a < nact) { cells[a].vbase = ev; cells[a].fbase = ef; }
+    if (a < nact) { cells[a].vbase = ev; cells[a].fbase = ef; cells[a].cls = c.entry < 0 ? 0xffffu : ((uint32_t)c.entry | (c.owned << 16)); }
     if (threadIdx.x == 0) block_tot[blockIdx.x] = make_uint4(0, tv, tf, 0);
     if (c.ambiguous) atomicAdd(n_amb, 1ull);
     if (c.interior) atomicAdd(n_amb + 8, 1ull);
@@ -600,12 +673,17 @@ __global__ void __launch_bounds__(128) mc_list_verts_kernel(McParams p, const Ce
     const uint32_t a = blockIdx.x * 128 + threadIdx.x;
     if (a >= nact) return;
     CellRec r = cells[a];
+    if ((r.cls >> 16) == 0 || (r.cls & 0xffffu) == 0xffffu) return;      // no vertex of its own
     r.vbase += boff[a / MC_THREADS].y;
     int i, j, k;
     cell_coords(p, (int64_t)r.lin, i, j, k);
     Cell c;
-    classify(p, i, j, k, c);
-    if (c.nv) emit_cell_verts(p, o, i, j, k, c, (int64_t)r.vbase);
+    c.entry = (int)(r.cls & 0xffffu);
+    c.owned = r.cls >> 16;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        c.d[q] = __dsub_rn((double)__ldg(p.vol + node_lin(p, i + c_corner_off[3 * q], j + c_corner_off[3 * q + 1], k + c_corner_off[3 * q + 2])), p.level);
+    emit_cell_verts(p, o, i, j, k, c, (int64_t)r.vbase);
 }
 
 __global__ void __launch_bounds__(128) mc_list_faces_kernel(McParams p, const CellRec *__restrict__ cells, const uint4 *__restrict__ boff,
@@ -615,12 +693,15 @@ __global__ void __launch_bounds__(128) mc_list_faces_kernel(McParams p, const Ce
     const uint32_t a = blockIdx.x * 128 + threadIdx.x;
     if (a >= nact) return;
     CellRec r = cells[a];
+    if ((r.cls & 0xffffu) == 0xffffu) return;
     const uint4 bo = boff[a / MC_THREADS];
     r.vbase += bo.y; r.fbase += bo.z;
     int i, j, k;
     cell_coords(p, (int64_t)r.lin, i, j, k);
-    Cell c;
-    classify(p, i, j, k, c);
+    Cell c;                                                    // the volume is not read: entry and ownership come from the count pass
+    c.entry = (int)(r.cls & 0xffffu);
+    c.owned = r.cls >> 16;
+    c.nt = p.tb.ntri[c.entry];
     if (c.nt) emit_cell_faces(p, i, j, k, c, (int64_t)r.vbase, (int64_t)r.fbase, vid, seam_in, id_offset, faces, seam_bad);
 }
 
@@ -681,13 +762,45 @@ int surs_mc_init_tables(surs_ctx *ctx)
     return 0;
 }
 
+static int mc_count_impl(surs_ctx *ctx, const float *vol, const double *vol64, const int res[3], float level, int flags,
+                         int64_t *n_verts, int64_t *n_faces, int64_t *n_ambiguous, void *stream);
+
 extern "C" int surs_mc_count(surs_ctx *ctx, const float *vol, const int res[3], float level, int flags,
                              int64_t *n_verts, int64_t *n_faces, int64_t *n_ambiguous, void *stream)
+{
+    return mc_count_impl(ctx, vol, nullptr, res, level, flags, n_verts, n_faces, n_ambiguous, stream);
+}
+
+extern "C" int surs_mc_count_f64(surs_ctx *ctx, const double *vol64, float *vol32, const int res[3], float level, int flags,
+                                 int64_t *n_verts, int64_t *n_faces, int64_t *n_ambiguous, void *stream)
+{
+    if (ctx && !vol64) SURS_FAIL(ctx, "surs_mc_count_f64: null source volume");
+    return mc_count_impl(ctx, vol32, vol64, res, level, flags, n_verts, n_faces, n_ambiguous, stream);
+}
+
+extern "C" int surs_mc_value_range(surs_ctx *ctx, float *vmin, float *vmax)
+{
+    if (!ctx) return 1;
+    if (!ctx->mc_vol) SURS_FAIL(ctx, "surs_mc_value_range: call surs_mc_count first");
+    if (vmin) *vmin = ctx->mc_vmin;
+    if (vmax) *vmax = ctx->mc_vmax;
+    return 0;
+}
+
+// vol64 != NULL: the source is float64 and `vol` receives its float32 copy (made by the same pass that takes the bits)
+static int mc_count_impl(surs_ctx *ctx, const float *vol, const double *vol64, const int res[3], float level, int flags,
+                         int64_t *n_verts, int64_t *n_faces, int64_t *n_ambiguous, void *stream)
 {
     if (!ctx) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!vol || res[0] < 2 || res[1] < 2 || res[2] < 2) SURS_FAIL(ctx, "surs_mc_count: volume needs at least 2 nodes per axis");
+    float *vol_w = const_cast<float *>(vol);
+    unsigned *range = reinterpret_cast<unsigned *>(ctx->counter + 12);
+    {
+        const unsigned init[2] = {0xffffffffu, 0u};
+        SURS_CUDA(ctx, cudaMemcpyAsync(range, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
     const int64_t nnode = (int64_t)res[0] * res[1] * res[2];
     if (3 * nnode >= ((int64_t)1 << 31)) SURS_FAIL(ctx, "surs_mc_count: volume too large for 32-bit edge ids (3*res^3 < 2^31)");
     ctx->mc_vol = vol;
@@ -709,36 +822,48 @@ extern "C" int surs_mc_count(surs_ctx *ctx, const float *vol, const int res[3], 
         if (surs_ensure(ctx, (void **)&ctx->mc_bits, &ctx->mc_bits_cap, sizeof(uint32_t) * (size_t)nthr)) return 1;
         if (surs_ensure(ctx, (void **)&ctx->mc_block_tot, &ctx->mc_block_cap, sizeof(uint4) * (size_t)nbA)) return 1;
         uint32_t *bits = reinterpret_cast<uint32_t *>(ctx->mc_bits);
-        mc_sign_kernel<<<(unsigned)((nrows + MC_SIGN_WARPS - 1) / MC_SIGN_WARPS), MC_SIGN_WARPS * 32, 0, st>>>(vol, level, nrows, res[2], W, bits);
+        const unsigned sblocks = (unsigned)((nrows + MC_SIGN_WARPS - 1) / MC_SIGN_WARPS);
+        if (vol64) mc_sign_kernel<double, true><<<sblocks, MC_SIGN_WARPS * 32, 0, st>>>(vol64, vol_w, level, nrows, res[2], W, bits, range);
+        else mc_sign_kernel<float, false><<<sblocks, MC_SIGN_WARPS * 32, 0, st>>>(vol, nullptr, level, nrows, res[2], W, bits, range);
         SURS_LAUNCH_CHECK(ctx, "mc_sign_kernel");
         uint4 *btA = reinterpret_cast<uint4 *>(ctx->mc_block_tot);
-        mc_bits_kernel<false><<<(unsigned)nbA, MC_THREADS, 0, st>>>(p, bits, W, (uint32_t)nthr, btA, nullptr);
+        mc_bits_kernel<false><<<(unsigned)nbA, MC_THREADS, 0, st>>>(p, bits, W, (uint32_t)nthr, btA, nullptr, nullptr, 0);
         SURS_LAUNCH_CHECK(ctx, "mc_bits_kernel<count>");
         mc_scan_blocks3_kernel<<<1, 1024, 0, st>>>(btA, nbA, ctx->counter + 5);       // counter[7] = number of active cells
         SURS_LAUNCH_CHECK(ctx, "mc_scan_blocks3_kernel");
+        // compaction, per-cell classification and the second scan run on an ESTIMATE of the list length (the last
+        // volume's, at least 1/16 of the cells), so the whole count phase needs ONE host synchronisation; if the
+        // estimate was too small the kernels wrote nothing and the phase is repeated with the exact length
         unsigned long long host[8];
-        SURS_CUDA(ctx, cudaMemcpyAsync(host, ctx->counter, sizeof(host), cudaMemcpyDeviceToHost, st));
-        SURS_CUDA(ctx, cudaStreamSynchronize(st));
-        ctx->mc_nact = (int64_t)host[7];
-        ctx->mc_nv = ctx->mc_nf = 0;
-        host[1] = 0;
-        if (ctx->mc_nact > 0) {
-            const int64_t nbB = (ctx->mc_nact + MC_THREADS - 1) / MC_THREADS;
-            if (surs_ensure(ctx, (void **)&ctx->mc_cells, &ctx->mc_cells_cap, sizeof(CellRec) * (size_t)ctx->mc_nact)) return 1;
+        int64_t cap = ctx->mc_cap_hint > 0 ? ctx->mc_cap_hint + ctx->mc_cap_hint / 4 : 0;
+        if (cap < nnode / 16) cap = nnode / 16;
+        if (cap < 4096) cap = 4096;
+        if (cap > nnode) cap = nnode;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const int64_t nbB = (cap + MC_THREADS - 1) / MC_THREADS;
+            if (surs_ensure(ctx, (void **)&ctx->mc_cells, &ctx->mc_cells_cap, sizeof(CellRec) * (size_t)cap)) return 1;
             if (surs_ensure(ctx, (void **)&ctx->mc_cell_tot, &ctx->mc_cell_tot_cap, sizeof(uint4) * (size_t)nbB)) return 1;
             CellRec *cells = reinterpret_cast<CellRec *>(ctx->mc_cells);
             uint4 *btB = reinterpret_cast<uint4 *>(ctx->mc_cell_tot);
-            mc_bits_kernel<true><<<(unsigned)nbA, MC_THREADS, 0, st>>>(p, bits, W, (uint32_t)nthr, btA, cells);
+            mc_bits_kernel<true><<<(unsigned)nbA, MC_THREADS, 0, st>>>(p, bits, W, (uint32_t)nthr, btA, cells, ctx->counter + 7, (uint32_t)cap);
             SURS_LAUNCH_CHECK(ctx, "mc_bits_kernel<compact>");
-            mc_cell_kernel<<<(unsigned)nbB, MC_THREADS, 0, st>>>(p, cells, (uint32_t)ctx->mc_nact, btB, ctx->counter + 1);
+            mc_cell_kernel<<<(unsigned)nbB, MC_THREADS, 0, st>>>(p, cells, ctx->counter + 7, (uint32_t)cap, btB, ctx->counter + 1);
             SURS_LAUNCH_CHECK(ctx, "mc_cell_kernel");
             mc_scan_blocks3_kernel<<<1, 1024, 0, st>>>(btB, nbB, ctx->counter + 2);
             SURS_LAUNCH_CHECK(ctx, "mc_scan_blocks3_kernel");
             SURS_CUDA(ctx, cudaMemcpyAsync(host, ctx->counter, sizeof(host), cudaMemcpyDeviceToHost, st));
+            SURS_CUDA(ctx, cudaMemcpyAsync(ctx->mc_range_host, range, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             SURS_CUDA(ctx, cudaStreamSynchronize(st));
-            ctx->mc_nv = (int64_t)host[2];
-            ctx->mc_nf = (int64_t)host[3];
+            ctx->mc_vmin = key2f(ctx->mc_range_host[0]);
+            ctx->mc_vmax = key2f(ctx->mc_range_host[1]);
+            ctx->mc_nact = (int64_t)host[7];
+            if (ctx->mc_nact <= cap) break;
+            cap = ctx->mc_nact;                                                       // estimate too small: exact length now
+            host[7] = 0;
         }
+        ctx->mc_cap_hint = ctx->mc_nact;
+        ctx->mc_nv = ctx->mc_nact > 0 ? (int64_t)host[2] : 0;
+        ctx->mc_nf = ctx->mc_nact > 0 ? (int64_t)host[3] : 0;
         if (ctx->mc_nv >= ((int64_t)1 << 31) || ctx->mc_nf >= ((int64_t)1 << 31)) SURS_FAIL(ctx, "surs_mc_count: mesh too large for int32 indices");
         if (n_verts) *n_verts = ctx->mc_nv;
         if (n_faces) *n_faces = ctx->mc_nf;
@@ -747,13 +872,22 @@ extern "C" int surs_mc_count(surs_ctx *ctx, const float *vol, const int res[3], 
     }
     const int64_t nblocks = (nnode + MC_THREADS - 1) / MC_THREADS;
     if (surs_ensure(ctx, (void **)&ctx->mc_block_tot, &ctx->mc_block_cap, sizeof(uint2) * (size_t)nblocks)) return 1;
+    {
+        const unsigned rb = (unsigned)(nblocks < ctx->sm_count * 16 ? nblocks : ctx->sm_count * 16);
+        if (vol64) mc_range_kernel<double, true><<<rb, MC_THREADS, 0, st>>>(vol64, vol_w, nnode, range);
+        else mc_range_kernel<float, false><<<rb, MC_THREADS, 0, st>>>(vol, nullptr, nnode, range);
+        SURS_LAUNCH_CHECK(ctx, "mc_range_kernel");
+    }
     mc_count_kernel<<<(unsigned)nblocks, MC_THREADS, 0, st>>>(p, nnode, reinterpret_cast<uint2 *>(ctx->mc_block_tot), ctx->counter + 1);
     SURS_LAUNCH_CHECK(ctx, "mc_count_kernel");
     mc_scan_blocks_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<uint2 *>(ctx->mc_block_tot), nblocks, ctx->counter + 2);
     SURS_LAUNCH_CHECK(ctx, "mc_scan_blocks_kernel");
     unsigned long long host[4];
     SURS_CUDA(ctx, cudaMemcpyAsync(host, ctx->counter, sizeof(host), cudaMemcpyDeviceToHost, st));
+    SURS_CUDA(ctx, cudaMemcpyAsync(ctx->mc_range_host, range, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     SURS_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->mc_vmin = key2f(ctx->mc_range_host[0]);
+    ctx->mc_vmax = key2f(ctx->mc_range_host[1]);
     ctx->mc_nv = (int64_t)host[2];
     ctx->mc_nf = (int64_t)host[3];
     if (ctx->mc_nv >= ((int64_t)1 << 31) || ctx->mc_nf >= ((int64_t)1 << 31)) SURS_FAIL(ctx, "surs_mc_count: mesh too large for int32 indices");

@@ -22,12 +22,13 @@ from .. import _capi
 _MC_LEVEL = 0.5          # lib/mesh_util.py:40,45
 
 
-def _mesh_from_volume(ctx, vol_f32, mat):
-    """Device marching cubes + world transform; mirrors skimage's error behaviour."""
-    vmin, vmax = torch.aminmax(vol_f32)
-    if not (float(vmin) <= _MC_LEVEL <= float(vmax)):
+def _mesh_from_volume(ctx, vol, mat):
+    """Device marching cubes + world transform; mirrors skimage's error behaviour.  vol: fp32, or the octree's float64
+    volume (the float32 copy skimage makes and the value range it checks are by-products of the bit pass)."""
+    nv, nf, n_amb = ctx.mc_count(vol, _MC_LEVEL)
+    vmin, vmax = ctx.mc_value_range()
+    if not (vmin <= _MC_LEVEL <= vmax):
         raise ValueError("Surface level must be within volume data range.")
-    nv, nf, n_amb = ctx.mc_count(vol_f32, _MC_LEVEL)
     if nv == 0 or nf == 0:
         raise RuntimeError("No surface found at the given iso value.")
     verts, world, normals, values = ctx.mc_emit_verts(nv, mat)
@@ -81,8 +82,7 @@ def _reconstruction(opt, net, cuda, calib_tensor, resolution, b_min, b_max, use_
         if use_octree:
             hr64, lr64, n_eval = ctx.eval_grid_octree(res, b_min, b_max, calib_tensor, zn, zd, float(opt.threshold),
                                                       init_resolution=64, transform=transform, precision=prec)
-            vol_hr, vol_lr = ctx.cast_f64_f32(hr64), ctx.cast_f64_f32(lr64)
-            del hr64, lr64
+            vol_hr, vol_lr = hr64, lr64                 # float64: cast inside the marching-cubes bit pass
             stats["n_evaluated"] = n_eval
         else:
             vol_hr, vol_lr = ctx.eval_grid(res, b_min, b_max, calib_tensor, zn, zd, transform=transform, precision=prec)
@@ -150,10 +150,10 @@ def marching_cubes_lewiner(volume, level, device="cuda"):
     reference uses it (lib/mesh_util.py:40): numpy in, (verts, faces, normals, values) numpy out."""
     ctx = _default_context(device)
     vol = torch.from_numpy(np.ascontiguousarray(volume, dtype=np.float32)).to(ctx.device)
-    vmin, vmax = float(vol.min()), float(vol.max())
+    verts, _, faces, normals, values, _ = ctx.marching_cubes(vol, level)
+    vmin, vmax = ctx.mc_value_range()
     if not (vmin <= level <= vmax):
         raise ValueError("Surface level must be within volume data range.")
-    verts, _, faces, normals, values, _ = ctx.marching_cubes(vol, level)
     if verts.shape[0] == 0 or faces.shape[0] == 0:
         raise RuntimeError("No surface found at the given iso value.")
     return verts.cpu().numpy(), faces.cpu().numpy(), normals.cpu().numpy(), values.cpu().numpy()

@@ -299,6 +299,34 @@ def test_marching_cubes_passes_the_table_free_checker(ctx):
     assert rep["orientation_wrong"] == 0 and rep["border_edges"] == 0
 
 
+def test_marching_cubes_float64_source_and_value_range(ctx):
+    """The bit pass also yields what skimage derives from every value: the float32 copy of a float64 volume (octree
+    volumes stay float64, lib/sdf.py:60-61) and the value range the level is checked against -- fast and general path."""
+    rng = np.random.default_rng(7)
+    for shape in ((20, 24, 64), (9, 10, 27)):
+        v64 = torch.from_numpy(rng.random(shape) * 1.3 - 0.2).to(ctx.device)
+        v32 = v64.float()
+        a = ctx.mc_count(v64, 0.5)
+        ra = ctx.mc_value_range()
+        va, _, _, _ = ctx.mc_emit_verts(a[0])
+        fa = ctx.mc_emit_faces(a[1])
+        assert torch.equal(ctx._mc_vol, v32)
+        b = ctx.mc_count(v32, 0.5)
+        rb = ctx.mc_value_range()
+        vb, _, _, _ = ctx.mc_emit_verts(b[0])
+        fb = ctx.mc_emit_faces(b[1])
+        assert a == b and torch.equal(va, vb) and torch.equal(fa, fb)
+        assert ra == rb == (float(v32.min()), float(v32.max()))
+    # repeated volumes of very different surface size: the list-length estimate of the previous call must not matter
+    big = torch.from_numpy(rng.random((32, 32, 64)).astype(np.float32)).to(ctx.device)
+    small = torch.from_numpy(helpers.sphere_volume(64, 5.0)[:32, :32]).to(ctx.device).contiguous()
+    want_big, want_small = None, None
+    for vol in (small, big, small, big):
+        got = ctx.marching_cubes(vol, 0.5)
+        ref = mc_oracle.marching_cubes_lewiner(vol.cpu().numpy(), 0.5) if vol is big or got[0].shape[0] else None
+        assert np.array_equal(got[2].cpu().numpy(), ref[1]) and np.array_equal(got[0].cpu().numpy(), ref[0])
+
+
 def test_marching_cubes_slabs_reproduce_single_volume(ctx):
     """Three slabs with the seam protocol (SURS_MC_LOWER_FOREIGN + seam maps) == one volume."""
     from surs_b200 import _capi
