@@ -287,6 +287,65 @@ __device__ __forceinline__ void write_vertex(const McOut &o, int64_t v, const do
     if (o.values) o.values[v] = (float)value;
 }
 
+// rank of vertex slot `slot` (0..11 cube edges, 12 centre) among the slots this cell creates, in first-use order
+__device__ __forceinline__ int owned_rank(const uint8_t *rank, unsigned owned, int slot)
+{
+    int r = 0;
+    for (int e2 = 0; e2 < 13; ++e2)
+        if (((owned >> e2) & 1u) && rank[e2] < rank[slot]) ++r;
+    return r;
+}
+
+// the vertex on cube edge e of cell (i,j,k): da / db = value - level at the edge's lower / upper end
+__device__ __forceinline__ void emit_edge_vertex(const McParams &p, const McOut &o, int i, int j, int k, int e, double dlo, double dhi, int64_t v)
+{
+    const int axis = c_edge_axis[e];
+    const int bi = i + c_edge_base[3 * e], bj = j + c_edge_base[3 * e + 1], bk = k + c_edge_base[3 * e + 2];
+    const int ei = bi + (axis == 0), ej = bj + (axis == 1), ek = bk + (axis == 2);
+    double pos[3] = {(double)(bi + o.plane_offset), (double)bj, (double)bk};
+    const double base = pos[axis];
+    const double x = edge_point(base, dlo, dhi);
+    pos[axis] = x;
+    double g[3] = {0.0, 0.0, 0.0};
+    if (o.normals) {
+        const double tt = x - base;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double ga = node_grad(p, bi, bj, bk, a), gb = node_grad(p, ei, ej, ek, a);
+            g[a] = ga + tt * (gb - ga);
+        }
+    }
+    const double va = (double)__ldg(p.vol + node_lin(p, bi, bj, bk)), vb = (double)__ldg(p.vol + node_lin(p, ei, ej, ek));
+    write_vertex(o, v, pos, g, va > vb ? va : vb);
+    o.vid[3 * node_lin(p, bi, bj, bk) + axis] = (int32_t)(v + o.id_offset);
+}
+
+// Lewiner's centre vertex: mean of the cell's edge vertices; d[q] = value - level at corner q
+__device__ __forceinline__ void emit_centre_vertex(const McParams &p, const McOut &o, int i, int j, int k, const double (&d)[8], int64_t v)
+{
+    double s[3] = {0.0, 0.0, 0.0};
+    int n = 0;
+    for (int e = 0; e < 12; ++e) {
+        const int ca = c_edge_corner[2 * e], cb = c_edge_corner[2 * e + 1];
+        if ((d[ca] > 0.0) == (d[cb] > 0.0)) continue;
+        const int axis = c_edge_axis[e];
+        const int lo = c_corner_off[3 * ca + axis] == 0 ? ca : cb, hi = lo == ca ? cb : ca;
+        double q[3] = {(double)(i + o.plane_offset + c_edge_base[3 * e]), (double)(j + c_edge_base[3 * e + 1]), (double)(k + c_edge_base[3 * e + 2])};
+        q[axis] = edge_point(q[axis], d[lo], d[hi]);
+        s[0] = __dadd_rn(s[0], q[0]); s[1] = __dadd_rn(s[1], q[1]); s[2] = __dadd_rn(s[2], q[2]);
+        ++n;
+    }
+    double pos[3] = {__ddiv_rn(s[0], (double)n), __ddiv_rn(s[1], (double)n), __ddiv_rn(s[2], (double)n)};
+    double g[3] = {0.0, 0.0, 0.0}, vmax = -INFINITY;
+    for (int q = 0; q < 8; ++q) {
+        const int ci = i + c_corner_off[3 * q], cj = j + c_corner_off[3 * q + 1], ck = k + c_corner_off[3 * q + 2];
+        if (o.normals)
+            for (int a = 0; a < 3; ++a) g[a] += node_grad(p, ci, cj, ck, a);
+        vmax = fmax(vmax, (double)__ldg(p.vol + node_lin(p, ci, cj, ck)));
+    }
+    write_vertex(o, v, pos, g, vmax);
+}
+
 // all vertices created by cell (i,j,k); vbase = index of its first vertex in this volume's list
 __device__ __forceinline__ void emit_cell_verts(const McParams &p, const McOut &o, int i, int j, int k, const Cell &c, int64_t vbase)
 {
@@ -294,58 +353,12 @@ __device__ __forceinline__ void emit_cell_verts(const McParams &p, const McOut &
 #pragma unroll 1
     for (int e = 0; e < 12; ++e) {
         if (!((c.owned >> e) & 1u)) continue;
-        int r = 0;
-        for (int e2 = 0; e2 < 13; ++e2)
-            if (((c.owned >> e2) & 1u) && rank[e2] < rank[e]) ++r;
-        const int64_t v = vbase + r;
         const int axis = c_edge_axis[e];
-        const int bi = i + c_edge_base[3 * e], bj = j + c_edge_base[3 * e + 1], bk = k + c_edge_base[3 * e + 2];
-        const int ei = bi + (axis == 0), ej = bj + (axis == 1), ek = bk + (axis == 2);
         const int ca = c_edge_corner[2 * e], cb = c_edge_corner[2 * e + 1];
         const int lo = c_corner_off[3 * ca + axis] == 0 ? ca : cb, hi = lo == ca ? cb : ca;
-        double pos[3] = {(double)(bi + o.plane_offset), (double)bj, (double)bk};
-        const double base = pos[axis];
-        const double x = edge_point(base, c.d[lo], c.d[hi]);
-        pos[axis] = x;
-        double g[3] = {0.0, 0.0, 0.0};
-        if (o.normals) {
-            const double tt = x - base;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const double ga = node_grad(p, bi, bj, bk, a), gb = node_grad(p, ei, ej, ek, a);
-                g[a] = ga + tt * (gb - ga);
-            }
-        }
-        const double va = (double)__ldg(p.vol + node_lin(p, bi, bj, bk)), vb = (double)__ldg(p.vol + node_lin(p, ei, ej, ek));
-        write_vertex(o, v, pos, g, va > vb ? va : vb);
-        o.vid[3 * node_lin(p, bi, bj, bk) + axis] = (int32_t)(v + o.id_offset);
+        emit_edge_vertex(p, o, i, j, k, e, c.d[lo], c.d[hi], vbase + owned_rank(rank, c.owned, e));
     }
-    if ((c.owned >> 12) & 1u) {                  // centre vertex: mean of the cell's edge vertices
-        int r = 0;
-        for (int e2 = 0; e2 < 12; ++e2)
-            if (((c.owned >> e2) & 1u) && rank[e2] < rank[12]) ++r;
-        double s[3] = {0.0, 0.0, 0.0};
-        int n = 0;
-        for (int e = 0; e < 12; ++e) {
-            const int ca = c_edge_corner[2 * e], cb = c_edge_corner[2 * e + 1];
-            if ((c.d[ca] > 0.0) == (c.d[cb] > 0.0)) continue;
-            const int axis = c_edge_axis[e];
-            const int lo = c_corner_off[3 * ca + axis] == 0 ? ca : cb, hi = lo == ca ? cb : ca;
-            double q[3] = {(double)(i + o.plane_offset + c_edge_base[3 * e]), (double)(j + c_edge_base[3 * e + 1]), (double)(k + c_edge_base[3 * e + 2])};
-            q[axis] = edge_point(q[axis], c.d[lo], c.d[hi]);
-            s[0] = __dadd_rn(s[0], q[0]); s[1] = __dadd_rn(s[1], q[1]); s[2] = __dadd_rn(s[2], q[2]);
-            ++n;
-        }
-        double pos[3] = {__ddiv_rn(s[0], (double)n), __ddiv_rn(s[1], (double)n), __ddiv_rn(s[2], (double)n)};
-        double g[3] = {0.0, 0.0, 0.0}, vmax = -INFINITY;
-        for (int q = 0; q < 8; ++q) {
-            const int ci = i + c_corner_off[3 * q], cj = j + c_corner_off[3 * q + 1], ck = k + c_corner_off[3 * q + 2];
-            if (o.normals)
-                for (int a = 0; a < 3; ++a) g[a] += node_grad(p, ci, cj, ck, a);
-            vmax = fmax(vmax, (double)__ldg(p.vol + node_lin(p, ci, cj, ck)));
-        }
-        write_vertex(o, vbase + r, pos, g, vmax);
-    }
+    if ((c.owned >> 12) & 1u) emit_centre_vertex(p, o, i, j, k, c.d, vbase + owned_rank(rank, c.owned, 12));
 }
 
 __global__ void __launch_bounds__(MC_THREADS) mc_emit_verts_kernel(McParams p, int64_t nnode, const uint2 *block_prefix, McOut o)
@@ -474,46 +487,82 @@ __host__ __device__ __forceinline__ float key2f(unsigned k)
 // (what skimage checks the level against: replaces a separate aminmax pass) and, for a float64 source (octree volumes,
 // lib/sdf.py keeps them in float64), the float32 copy that skimage makes of its input (replaces a separate cast pass).
 // range[0] / range[1]: ordered keys of the minimum / maximum, updated with one guarded atomic per warp.
+// sixteen streaming loads, 32 elements apart, issued back to back (one asm block per eight: the compiler otherwise
+// interleaves the range arithmetic with the loads and halves the memory-level parallelism)
+__device__ __forceinline__ void load16_cs(const float *p, float (&r)[16])
+{
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        asm volatile("ld.global.cs.f32 %0, [%8];\n\tld.global.cs.f32 %1, [%8+128];\n\tld.global.cs.f32 %2, [%8+256];\n\t"
+                     "ld.global.cs.f32 %3, [%8+384];\n\tld.global.cs.f32 %4, [%8+512];\n\tld.global.cs.f32 %5, [%8+640];\n\t"
+                     "ld.global.cs.f32 %6, [%8+768];\n\tld.global.cs.f32 %7, [%8+896];"
+                     : "=f"(r[8 * h]), "=f"(r[8 * h + 1]), "=f"(r[8 * h + 2]), "=f"(r[8 * h + 3]), "=f"(r[8 * h + 4]), "=f"(r[8 * h + 5]),
+                       "=f"(r[8 * h + 6]), "=f"(r[8 * h + 7])
+                     : "l"(p + 256 * h));
+}
+__device__ __forceinline__ void load16_cs(const double *p, double (&r)[16])
+{
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        asm volatile("ld.global.cs.f64 %0, [%8];\n\tld.global.cs.f64 %1, [%8+256];\n\tld.global.cs.f64 %2, [%8+512];\n\t"
+                     "ld.global.cs.f64 %3, [%8+768];\n\tld.global.cs.f64 %4, [%8+1024];\n\tld.global.cs.f64 %5, [%8+1280];\n\t"
+                     "ld.global.cs.f64 %6, [%8+1536];\n\tld.global.cs.f64 %7, [%8+1792];"
+                     : "=d"(r[8 * h]), "=d"(r[8 * h + 1]), "=d"(r[8 * h + 2]), "=d"(r[8 * h + 3]), "=d"(r[8 * h + 4]), "=d"(r[8 * h + 5]),
+                       "=d"(r[8 * h + 6]), "=d"(r[8 * h + 7])
+                     : "l"(p + 256 * h));
+}
+
 template <typename T, bool COPY32>
 __global__ void __launch_bounds__(MC_SIGN_WARPS * 32) mc_sign_kernel(const T *__restrict__ vol, float *__restrict__ vol32, float level, int64_t nrows,
                                                                       int R2, int W, uint32_t *__restrict__ bits, unsigned *__restrict__ range)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * MC_SIGN_WARPS + (threadIdx.x >> 5);
-    if (row >= nrows) return;
-    const T *src = vol + row * R2;
-    uint32_t *dst = bits + row * W;
+    // persistent warps: a warp walks rows with the grid's warp count as stride, so the value range costs one
+    // reduction per warp and one guarded atomic per block for the whole volume, not per row
+    __shared__ unsigned s_lo[MC_SIGN_WARPS], s_hi[MC_SIGN_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float lo = INFINITY, hi = -INFINITY;
-    for (int w0 = 0; w0 < W; w0 += 16) {
-        float v[16];
+    for (int64_t row = (int64_t)blockIdx.x * MC_SIGN_WARPS + warp; row < nrows; row += (int64_t)gridDim.x * MC_SIGN_WARPS) {
+        const T *src = vol + row * R2;
+        uint32_t *dst = bits + row * W;
+        for (int w0 = 0; w0 < W; w0 += 16) {
+            T raw[16];
+            if ((w0 + 16) * 32 <= R2) {
+                load16_cs(src + w0 * 32 + lane, raw);                    // streamed: nothing re-reads the source from L1
+            } else {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int k = (w0 + u) * 32 + lane;
-            const bool ok = w0 + u < W && k < R2;
-            v[u] = ok ? (float)__ldcs(src + k) : level;                  // streamed: nothing re-reads the source from L1
-            if (ok) {
-                lo = fminf(lo, v[u]);
-                hi = fmaxf(hi, v[u]);
-                if (COPY32) vol32[row * R2 + k] = v[u];
+                for (int u = 0; u < 16; ++u) {
+                    const int k = (w0 + u) * 32 + lane;
+                    raw[u] = (w0 + u < W && k < R2) ? __ldcs(src + k) : (T)level;
+                }
             }
-        }
-        uint32_t mine = 0;
+            float v[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const uint32_t word = __ballot_sync(0xffffffffu, v[u] > level);
-            if (lane == u) mine = word;
-        }
-        if (lane < 16 && w0 + lane < W) dst[w0 + lane] = mine;
-    }
+            for (int u = 0; u < 16; ++u) {
+                const int k = (w0 + u) * 32 + lane;
+                const bool ok = w0 + u < W && k < R2;
+                v[u] = (float)raw[u];
+                if (COPY32 && ok) vol32[row * R2 + k] = v[u];
+                lo = fminf(lo, ok ? v[u] : lo);                          // (selects, no branches: padding lanes do not count)
+                hi = fmaxf(hi, ok ? v[u] : hi);
+            }
+            uint32_t mine = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            for (int u = 0; u < 16; ++u) {
+                const uint32_t word = __ballot_sync(0xffffffffu, v[u] > level);
+                if (lane == u) mine = word;
+            }
+            if (lane < 16 && w0 + lane < W) dst[w0 + lane] = mine;
+        }
     }
-    if (lane == 0) {                                                     // after the first rows the guards almost never pass
-        const unsigned klo = f2key(lo), khi = f2key(hi);
-        if (klo < __ldcg(range)) atomicMin(range, klo);
-        if (khi > __ldcg(range + 1)) atomicMax(range + 1, khi);
+    const unsigned klo = __reduce_min_sync(0xffffffffu, f2key(lo)), khi = __reduce_max_sync(0xffffffffu, f2key(hi));
+    if (lane == 0) { s_lo[warp] = klo; s_hi[warp] = khi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned a = s_lo[0], b = s_hi[0];
+#pragma unroll
+        for (int w = 1; w < MC_SIGN_WARPS; ++w) { a = min(a, s_lo[w]); b = max(b, s_hi[w]); }
+        if (a < __ldcg(range)) atomicMin(range, a);
+        if (b > __ldcg(range + 1)) atomicMax(range + 1, b);
     }
 }
 
@@ -633,17 +682,31 @@ __global__ void __launch_bounds__(MC_THREADS) mc_cell_kernel(McParams p, CellRec
     if (c.interior == 2) atomicAdd(n_amb + 9, 1ull);
 }
 
-__global__ void __launch_bounds__(1024) mc_scan_blocks3_kernel(uint4 *block_tot, int64_t nblocks, unsigned long long *totals)
+// single-CTA exclusive scan of (x, y, z) over the per-block totals: every thread owns SCAN_ITEMS consecutive entries, so
+// 32 K entries take four rounds of (warp scan, one barrier pair) instead of thirty-two
+constexpr int SCAN_ITEMS = 8;
+__global__ void __launch_bounds__(1024) mc_scan_blocks3_kernel(uint4 *block_tot, int64_t nblocks, unsigned long long *totals,
+                                                               const unsigned long long *nitems, int per_block)
 {
+    if (nitems) {                                    // the list was sized by an estimate: only ceil(n / per_block) blocks hold cells
+        const int64_t used = (int64_t)((*nitems + per_block - 1) / per_block);
+        nblocks = used < nblocks ? used : nblocks;
+    }
     __shared__ unsigned long long wsum[3][32];
     __shared__ unsigned long long carry[3];
     if (threadIdx.x < 3) carry[threadIdx.x] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < nblocks; base += 1024) {
-        const int64_t idx = base + threadIdx.x;
-        const uint4 v = idx < nblocks ? block_tot[idx] : make_uint4(0, 0, 0, 0);
-        unsigned long long a[3] = {v.x, v.y, v.z};
+    for (int64_t base = 0; base < nblocks; base += 1024 * SCAN_ITEMS) {
+        const int64_t first = base + (int64_t)threadIdx.x * SCAN_ITEMS;
+        uint4 v[SCAN_ITEMS];
+        unsigned long long a[3] = {0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS; ++q) {
+            v[q] = first + q < nblocks ? block_tot[first + q] : make_uint4(0, 0, 0, 0);
+            a[0] += v[q].x; a[1] += v[q].y; a[2] += v[q].z;
+        }
+        const unsigned long long mine[3] = {a[0], a[1], a[2]};
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1)
 #pragma unroll
@@ -657,8 +720,12 @@ __global__ void __launch_bounds__(1024) mc_scan_blocks3_kernel(uint4 *block_tot,
         unsigned long long off[3] = {carry[0], carry[1], carry[2]};
         for (int w = 0; w < warp; ++w)
             for (int c = 0; c < 3; ++c) off[c] += wsum[c][w];
-        if (idx < nblocks)
-            block_tot[idx] = make_uint4((unsigned)(off[0] + a[0] - v.x), (unsigned)(off[1] + a[1] - v.y), (unsigned)(off[2] + a[2] - v.z), 0);
+        unsigned long long run[3] = {off[0] + a[0] - mine[0], off[1] + a[1] - mine[1], off[2] + a[2] - mine[2]};
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS; ++q) {
+            if (first + q < nblocks) block_tot[first + q] = make_uint4((unsigned)run[0], (unsigned)run[1], (unsigned)run[2], 0);
+            run[0] += v[q].x; run[1] += v[q].y; run[2] += v[q].z;
+        }
         __syncthreads();
         if (threadIdx.x == 1023)
             for (int c = 0; c < 3; ++c) carry[c] = off[c] + a[c];
@@ -667,6 +734,8 @@ __global__ void __launch_bounds__(1024) mc_scan_blocks3_kernel(uint4 *block_tot,
     if (threadIdx.x == 0) { totals[0] = carry[1]; totals[1] = carry[2]; totals[2] = carry[0]; }
 }
 
+// one thread per active cell (four threads per cell, one per owned edge, measured SLOWER: 465 vs 290 us at 512^3 --
+// the cell record, the rank table and the gradient taps are then fetched four times)
 __global__ void __launch_bounds__(128) mc_list_verts_kernel(McParams p, const CellRec *__restrict__ cells, const uint4 *__restrict__ boff,
                                                             uint32_t nact, McOut o)
 {
@@ -822,14 +891,16 @@ static int mc_count_impl(surs_ctx *ctx, const float *vol, const double *vol64, c
         if (surs_ensure(ctx, (void **)&ctx->mc_bits, &ctx->mc_bits_cap, sizeof(uint32_t) * (size_t)nthr)) return 1;
         if (surs_ensure(ctx, (void **)&ctx->mc_block_tot, &ctx->mc_block_cap, sizeof(uint4) * (size_t)nbA)) return 1;
         uint32_t *bits = reinterpret_cast<uint32_t *>(ctx->mc_bits);
-        const unsigned sblocks = (unsigned)((nrows + MC_SIGN_WARPS - 1) / MC_SIGN_WARPS);
+        int64_t sb = (nrows + MC_SIGN_WARPS - 1) / MC_SIGN_WARPS;
+        if (sb > (int64_t)ctx->sm_count * 8 * 8) sb = (int64_t)ctx->sm_count * 8 * 8;   // 8 resident CTAs per SM, 8 rows in flight per warp slot
+        const unsigned sblocks = (unsigned)sb;
         if (vol64) mc_sign_kernel<double, true><<<sblocks, MC_SIGN_WARPS * 32, 0, st>>>(vol64, vol_w, level, nrows, res[2], W, bits, range);
         else mc_sign_kernel<float, false><<<sblocks, MC_SIGN_WARPS * 32, 0, st>>>(vol, nullptr, level, nrows, res[2], W, bits, range);
         SURS_LAUNCH_CHECK(ctx, "mc_sign_kernel");
         uint4 *btA = reinterpret_cast<uint4 *>(ctx->mc_block_tot);
         mc_bits_kernel<false><<<(unsigned)nbA, MC_THREADS, 0, st>>>(p, bits, W, (uint32_t)nthr, btA, nullptr, nullptr, 0);
         SURS_LAUNCH_CHECK(ctx, "mc_bits_kernel<count>");
-        mc_scan_blocks3_kernel<<<1, 1024, 0, st>>>(btA, nbA, ctx->counter + 5);       // counter[7] = number of active cells
+        mc_scan_blocks3_kernel<<<1, 1024, 0, st>>>(btA, nbA, ctx->counter + 5, nullptr, 0);       // counter[7] = number of active cells
         SURS_LAUNCH_CHECK(ctx, "mc_scan_blocks3_kernel");
         // compaction, per-cell classification and the second scan run on an ESTIMATE of the list length (the last
         // volume's, at least 1/16 of the cells), so the whole count phase needs ONE host synchronisation; if the
@@ -849,7 +920,7 @@ static int mc_count_impl(surs_ctx *ctx, const float *vol, const double *vol64, c
             SURS_LAUNCH_CHECK(ctx, "mc_bits_kernel<compact>");
             mc_cell_kernel<<<(unsigned)nbB, MC_THREADS, 0, st>>>(p, cells, ctx->counter + 7, (uint32_t)cap, btB, ctx->counter + 1);
             SURS_LAUNCH_CHECK(ctx, "mc_cell_kernel");
-            mc_scan_blocks3_kernel<<<1, 1024, 0, st>>>(btB, nbB, ctx->counter + 2);
+            mc_scan_blocks3_kernel<<<1, 1024, 0, st>>>(btB, nbB, ctx->counter + 2, ctx->counter + 7, MC_THREADS);
             SURS_LAUNCH_CHECK(ctx, "mc_scan_blocks3_kernel");
             SURS_CUDA(ctx, cudaMemcpyAsync(host, ctx->counter, sizeof(host), cudaMemcpyDeviceToHost, st));
             SURS_CUDA(ctx, cudaMemcpyAsync(ctx->mc_range_host, range, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
