@@ -377,7 +377,8 @@ def run_ours(args):
     col_flop = 2 * 2 * (512 * 1024 + 256 * 512 + 128 * 256)
     one_ms = grid_ms(_capi.PREC_FP16) if prec == _capi.PREC_FP16R else None
     refined_frac = (refine["nodes"] / float(n_slab)) if refine else 0.0
-    executed_flop = {_capi.PREC_FP16: col_flop, _capi.PREC_FP16R: col_flop * (1.0 + 3.0 * refined_frac),
+    lr_only_frac = (refine["nodes_lr_mlp_only"] / float(n_slab)) if refine else 0.0
+    executed_flop = {_capi.PREC_FP16: col_flop, _capi.PREC_FP16R: col_flop * (1.0 + 3.0 * (refined_frac - 0.5 * lr_only_frac)),
                      _capi.PREC_FP16X3: 3 * col_flop}.get(prec, FLOP_PER_QUERY)
     achieved = n_slab * FLOP_PER_QUERY / (q_ms * 1e-3) / 1e12
     executed = n_slab * executed_flop / (q_ms * 1e-3) / 1e12

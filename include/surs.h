@@ -54,10 +54,11 @@ enum {
 int surs_version(void);
 /* nodes re-evaluated with split operands by the last surs_eval_grid(SURS_PREC_FP16R) of this context */
 int64_t surs_refined_nodes(const surs_ctx *ctx);
-/* ... and the run-time check of the band: max |one-pass - split| over those nodes, the band, and whether the check
- * failed (max_diff >= 0.8 band), in which case the whole slab was re-evaluated with SURS_PREC_FP16X3.  Any pointer
- * may be NULL. */
-int surs_refine_stats(const surs_ctx *ctx, int64_t *nodes, float *max_diff, float *band, int *fell_back);
+/* ... how many of them only the LR surface depends on (those go through the LR MLP alone; the HR MLP needs the LR
+ * prediction as an input, so nodes of the HR surface take both), and the run-time check of the band: max |one-pass -
+ * split| over the re-evaluated values, the band, and whether the check failed (max_diff >= 0.8 band), in which case the
+ * whole slab was re-evaluated with SURS_PREC_FP16X3.  Any pointer may be NULL. */
+int surs_refine_stats(const surs_ctx *ctx, int64_t *nodes, int64_t *nodes_lr_only, float *max_diff, float *band, int *fell_back);
 
 /* Lifetime.  `device` is a CUDA ordinal. */
 int surs_create(surs_ctx **out, int device);

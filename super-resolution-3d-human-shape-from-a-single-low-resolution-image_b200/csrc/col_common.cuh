@@ -65,5 +65,6 @@ static_assert(OFF_XW % 1024 == 0 && OFF_TABLE % 1024 == 0, "operand blocks must 
 int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo, int64_t ncols, cudaStream_t st, int passes = 1, int64_t point0 = -1);
 int surs_launch_query_generic_x3(surs_ctx *ctx, const PointIO &io, cudaStream_t st);
 // col0: first grid column of the resident table (0 for the whole-grid table of the octree, plane_lo * R1 for a slab's)
-int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int R2, cudaStream_t st, int passes = 1, int64_t col0 = 0);
+// nmlp = 1: only the LR MLP runs and only the LR volume is written (vol32 scatter)
+int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int R2, cudaStream_t st, int passes = 1, int64_t col0 = 0, int nmlp = 2);
 int surs_launch_query_inc(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st);

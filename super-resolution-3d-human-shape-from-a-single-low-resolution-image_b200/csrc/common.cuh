@@ -94,6 +94,18 @@ __device__ __forceinline__ void pointio_store(const PointIO &io, int64_t n, floa
     }
 }
 
+// refinement of a node that only the LR surface depends on: the LR volume alone is rewritten
+__device__ __forceinline__ void pointio_store_lr(const PointIO &io, int64_t n, float lr)
+{
+    if (!io.vol32_lr) return;
+    const int64_t lin = (io.idx_list ? io.idx_list[n] : io.lin_base + n) - io.vol32_base;
+    if (io.refine_maxdiff) {
+        const unsigned b = __float_as_uint(fabsf(io.vol32_lr[lin] - lr));
+        if (b > __ldcg(io.refine_maxdiff)) atomicMax(io.refine_maxdiff, b);
+    }
+    io.vol32_lr[lin] = lr;
+}
+
 // lib/geometry.py:15-31 + lib/model/SuRSNet.py:142 + lib/model/DepthNormalizer.py:18
 struct Projected {
     float u, v, zf, mask;
@@ -157,6 +169,7 @@ struct surs_ctx {
     char err[512];
     int64_t launches;
     int64_t refined_nodes;                 // SURS_PREC_FP16R: nodes re-evaluated by the last surs_eval_grid
+    int64_t refined_lr_only;               // ... of which only the LR surface depends on (LR MLP alone)
     float refine_maxdiff;                  // ... max |one-pass - split| over them
     int refine_fallback;                   // ... 1: the band check failed and the whole slab was re-evaluated with split operands
     void *mc_count_stream;                 // stream of the last surs_mc_count (surs_mc_interior_stats)
@@ -271,6 +284,6 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
 int surs_launch_query_inc(surs_ctx *ctx, const PointIO &io, int R1, int R2, int plane_lo, int nplanes, cudaStream_t st);
 // grid.cu
 int surs_refine_select_impl(surs_ctx *ctx, const float *hr, const float *lr, int np, int R1, int R2, int64_t lin_base,
-                            float level, float band, int64_t *idx, int64_t *n_selected, cudaStream_t st);
+                            float level, float band, int64_t *idx_both, int64_t *idx_lr_only, int64_t *n_both, int64_t *n_lr_only, cudaStream_t st);
 // mc.cu
 int surs_mc_init_tables(surs_ctx *ctx);

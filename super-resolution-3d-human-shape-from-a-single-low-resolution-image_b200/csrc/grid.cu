@@ -68,23 +68,26 @@ __global__ void __launch_bounds__(SEL_THREADS) octree_select_kernel(uint8_t *__r
 // SURS_PREC_FP16R: nodes of a dense slab [np, R1, R2] whose one-pass value must be recomputed with split operands --
 // every node that marching cubes at `level` can interpolate from after the refinement: the node or one of its six
 // neighbours lies within `band` of the level (its inside / outside bit may still change), or its bit differs from a
-// neighbour's.  The list holds global linear node indices (slab-relative index + lin_base).
+// neighbour's.  The criterion is evaluated per volume: nodes the HR surface depends on go to `idx_both` (the HR MLP
+// takes the LR prediction as an input, so both MLPs are re-evaluated), nodes only the LR surface depends on go to
+// `idx_lr` (the LR MLP alone).  The lists hold global linear node indices (slab-relative index + lin_base).
 __global__ void __launch_bounds__(SEL_THREADS) refine_select_kernel(const float *__restrict__ hr, const float *__restrict__ lr,
-                                                                    int64_t *__restrict__ idx, unsigned long long *counter,
-                                                                    int np, int R1, int R2, int64_t lin_base, float level, float band)
+                                                                    int64_t *__restrict__ idx_both, int64_t *__restrict__ idx_lr,
+                                                                    unsigned long long *counter, int np, int R1, int R2, int64_t lin_base,
+                                                                    float level, float band)
 {
-    __shared__ unsigned warp_cnt[SEL_THREADS / 32];
-    __shared__ unsigned long long block_base;
+    __shared__ unsigned warp_cnt[2][SEL_THREADS / 32];
+    __shared__ unsigned long long block_base[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n = (int64_t)np * R1 * R2;
     const int64_t first = ((int64_t)blockIdx.x * SEL_THREADS * SEL_PER_THREAD) + (int64_t)warp * 32 * SEL_PER_THREAD;
-    unsigned ballots[SEL_PER_THREAD];
-    unsigned mine = 0;
+    unsigned ballots[2][SEL_PER_THREAD];
+    unsigned mine[2] = {0, 0};
     const int64_t s1 = R2, s0 = (int64_t)R1 * R2;
 #pragma unroll
     for (int r = 0; r < SEL_PER_THREAD; ++r) {
         const int64_t c = first + r * 32 + lane;
-        bool take = false;
+        bool take[2] = {false, false};
         if (c < n) {
             const int k = (int)(c % R2);
             const int64_t t = c / R2;
@@ -95,30 +98,37 @@ __global__ void __launch_bounds__(SEL_THREADS) refine_select_kernel(const float 
             for (int v = 0; v < 2; ++v) {
                 const float *vol = v ? lr : hr;
                 const float x = vol[c];
-                take = take || fabsf(x - level) < band;
+                bool tk = fabsf(x - level) < band;
 #pragma unroll
                 for (int q = 0; q < 6; ++q) {
                     const float y = vol[nb[q]];
-                    take = take || fabsf(y - level) < band || ((x > level) != (y > level));
+                    tk = tk || fabsf(y - level) < band || ((x > level) != (y > level));
                 }
+                take[v] = tk;
             }
         }
-        ballots[r] = __ballot_sync(0xffffffffu, take);
-        mine += __popc(ballots[r]);
+        ballots[0][r] = __ballot_sync(0xffffffffu, take[0]);
+        ballots[1][r] = __ballot_sync(0xffffffffu, take[1] && !take[0]);
+        mine[0] += __popc(ballots[0][r]);
+        mine[1] += __popc(ballots[1][r]);
     }
-    if (lane == 0) warp_cnt[warp] = mine;
+    if (lane == 0) { warp_cnt[0][warp] = mine[0]; warp_cnt[1][warp] = mine[1]; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 2) {
         unsigned tot = 0;
-        for (int w = 0; w < SEL_THREADS / 32; ++w) { unsigned c = warp_cnt[w]; warp_cnt[w] = tot; tot += c; }
-        block_base = tot ? atomicAdd(counter, (unsigned long long)tot) : 0ull;
+        for (int w = 0; w < SEL_THREADS / 32; ++w) { unsigned c = warp_cnt[threadIdx.x][w]; warp_cnt[threadIdx.x][w] = tot; tot += c; }
+        block_base[threadIdx.x] = tot ? atomicAdd(counter + threadIdx.x, (unsigned long long)tot) : 0ull;
     }
     __syncthreads();
-    unsigned long long o = block_base + warp_cnt[warp];
 #pragma unroll
-    for (int r = 0; r < SEL_PER_THREAD; ++r) {
-        if ((ballots[r] >> lane) & 1u) idx[o + __popc(ballots[r] & ((1u << lane) - 1u))] = lin_base + first + r * 32 + lane;
-        o += __popc(ballots[r]);
+    for (int l = 0; l < 2; ++l) {
+        int64_t *idx = l ? idx_lr : idx_both;
+        unsigned long long o = block_base[l] + warp_cnt[l][warp];
+#pragma unroll
+        for (int r = 0; r < SEL_PER_THREAD; ++r) {
+            if ((ballots[l][r] >> lane) & 1u) idx[o + __popc(ballots[l][r] & ((1u << lane) - 1u))] = lin_base + first + r * 32 + lane;
+            o += __popc(ballots[l][r]);
+        }
     }
 }
 
@@ -212,17 +222,19 @@ int surs_octree_select_impl(surs_ctx *ctx, const int res[3], int reso, uint8_t *
 }
 
 int surs_refine_select_impl(surs_ctx *ctx, const float *hr, const float *lr, int np, int R1, int R2, int64_t lin_base,
-                            float level, float band, int64_t *idx, int64_t *n_selected, cudaStream_t st)
+                            float level, float band, int64_t *idx_both, int64_t *idx_lr_only, int64_t *n_both, int64_t *n_lr_only, cudaStream_t st)
 {
     const int64_t n = (int64_t)np * R1 * R2;
-    SURS_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned long long), st));
+    SURS_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, 2 * sizeof(unsigned long long), st));
     const int64_t per_block = SEL_THREADS * SEL_PER_THREAD;
-    refine_select_kernel<<<(unsigned)((n + per_block - 1) / per_block), SEL_THREADS, 0, st>>>(hr, lr, idx, ctx->counter, np, R1, R2, lin_base, level, band);
+    refine_select_kernel<<<(unsigned)((n + per_block - 1) / per_block), SEL_THREADS, 0, st>>>(hr, lr, idx_both, idx_lr_only, ctx->counter, np, R1, R2,
+                                                                                               lin_base, level, band);
     SURS_LAUNCH_CHECK(ctx, "refine_select_kernel");
-    unsigned long long c = 0;
-    SURS_CUDA(ctx, cudaMemcpyAsync(&c, ctx->counter, sizeof(c), cudaMemcpyDeviceToHost, st));
+    unsigned long long c[2] = {0, 0};
+    SURS_CUDA(ctx, cudaMemcpyAsync(c, ctx->counter, sizeof(c), cudaMemcpyDeviceToHost, st));
     SURS_CUDA(ctx, cudaStreamSynchronize(st));
-    *n_selected = (int64_t)c;
+    *n_both = (int64_t)c[0];
+    *n_lr_only = (int64_t)c[1];
     return 0;
 }
 

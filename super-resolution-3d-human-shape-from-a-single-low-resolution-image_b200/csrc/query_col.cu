@@ -82,6 +82,7 @@ struct ColParams {
     int64_t n0, n_end;             // MODE 2: the launch covers points [n0, n_end) of io
     int64_t col0;                  // MODE 1: the table starts at grid column col0 (a slab's table: plane_lo * R1)
     int ablate;                    // profiling only (SURS_COL_ABLATE): 1 = no weight traffic (results are garbage)
+    int nmlp;                      // 2: both MLPs; 1: the LR MLP only (refinement of nodes only the LR surface depends on)
 };
 
 // 32 consecutive channels of one row -> fp16 -> A ring slot.  v = acc + add + wz * zf + wp * pred.
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
             e.zf = pr.zf;
             float pred_lr = 0.0f;
 #pragma unroll 1
-            for (int m = 0; m < 2; ++m) {
+            for (int m = 0; m < prm.nmlp; ++m) {
                 const float *cvm = cv + m * CV_STRIDE, *gvm = gv_s + m * GV_STRIDE;
                 e.pred = pred_lr;
                 // layer 0 on the CUDA cores: 16 K blocks of y0 = leaky(C0 + w_z z (+ w_p pred_lr))
@@ -474,6 +475,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     if (m == 0) {
                         pred_lr = pred;
                         pred_x[e.row] = pred;
+                        if (INDEXED && prm.nmlp == 1 && n_own < (MODE == 2 ? prm.n_end : io.n)) pointio_store_lr(io, n_own, pred);
                     } else if (INDEXED) {
                         if (n_own < (MODE == 2 ? prm.n_end : io.n)) pointio_store(io, n_own, pred, pred_lr);
                     } else if (k < prm.R2) {
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 ++ablk;
             };
             for (int64_t tile = blockIdx.x; P != 1 && tile < prm.ntiles; tile += gridDim.x) {
-                for (int m = 0; m < 2; ++m) {
+                for (int m = 0; m < prm.nmlp; ++m) {
                     for (int half = 0; half < 2; ++half) {
                         // layer 1, one N half: K = 1024 -> T0
                         ptx::mbar_wait(&bars->acc_free[0], (acc0 & 1u) ^ 1u, 33, prof);
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 }
             }
             for (int64_t tile = blockIdx.x; P == 1 && tile < prm.ntiles; tile += gridDim.x) {
-                for (int m = 0; m < 2; ++m) {
+                for (int m = 0; m < prm.nmlp; ++m) {
                     long long tp = PROF ? clock64() : 0;
                     auto phase = [&](int slot) {
                         if (PROF) {
@@ -631,7 +633,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
             constexpr uint32_t IDESC256 = ptx::umma_idesc_f16(128, 256);
             uint32_t wblk = 1, ablk = 0, wph = 0, aph = 0, tph = 0;
             for (int64_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
-                for (int m = 0; m < 2; ++m) {
+                for (int m = 0; m < prm.nmlp; ++m) {
                     ptx::mbar_wait(&bars->t1_free_b, tph ^ 1u, 37, nullptr);          // E3 of the previous pass has read T1
                     tph ^= 1u;
                     ptx::tc_fence_after();
@@ -665,7 +667,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     ptx::tma_load_1d(smem + SMEM_CV + cvb * CV_BYTES, prm.table + (tile / prm.nseg) * CV_ROW_FLOATS, CV_BYTES, &bars->cv_full[cvb]);
                 }
                 const uint8_t *src = prm.weights;
-                for (int b = 0; b < 2 * BLOCKS_PER_MLP * RG::WP; ++b) {
+                for (int b = 0; b < prm.nmlp * BLOCKS_PER_MLP * RG::WP; ++b) {
                     const int bm = b % (BLOCKS_PER_MLP * RG::WP);
                     const uint32_t bytes = bm < 40 * RG::WP ? W_BLK_BYTES : W128_BLK_BYTES;
                     const uint32_t s = wblk % NSTAGE;
@@ -1128,6 +1130,7 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
     prm.R1 = R1; prm.R2 = R2; prm.plane_lo = plane_lo;
     prm.n0 = 0; prm.n_end = 0; prm.col0 = 0;
     prm.ablate = getenv("SURS_COL_ABLATE") ? atoi(getenv("SURS_COL_ABLATE")) : 0;
+    prm.nmlp = 2;
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
     static const bool profile = getenv("SURS_TC_PROFILE") != nullptr;
     if (passes == 3) {
@@ -1164,7 +1167,7 @@ int surs_launch_query_col(surs_ctx *ctx, const PointIO &io, int R1, int R2, int 
 // Octree levels through the column table: io is in grid mode with idx_list / vol_* set (n selected nodes of a
 // [R0, R1, R2] grid without transform); the table must cover all R0 x R1 columns (surs_col_build_table with
 // plane_lo = 0), built once per reconstruction.
-int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int R2, cudaStream_t st, int passes, int64_t col0)
+int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int R2, cudaStream_t st, int passes, int64_t col0, int nmlp)
 {
     if (io.n <= 0) return 0;
     uint8_t *base = (uint8_t *)ctx->col_weights;
@@ -1177,6 +1180,7 @@ int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int 
     prm.R1 = R1; prm.R2 = R2; prm.plane_lo = 0;
     prm.n0 = 0; prm.n_end = 0; prm.col0 = col0;
     prm.ablate = 0;
+    prm.nmlp = nmlp;
     const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
     if (passes == 3) {
         SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<3>::SMEM_TOTAL));
@@ -1210,6 +1214,7 @@ int surs_launch_query_generic_x3(surs_ctx *ctx, const PointIO &io, cudaStream_t 
         prm.R1 = 1; prm.R2 = 1; prm.plane_lo = 0;
         prm.n0 = s0; prm.n_end = s0 + len; prm.col0 = 0;
         prm.ablate = 0;
+    prm.nmlp = 2;
         const int grid = (int)(prm.ntiles < ctx->sm_count ? prm.ntiles : ctx->sm_count);
         SURS_CUDA(ctx, cudaFuncSetAttribute(query_col_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<3>::SMEM_TOTAL));
         query_col_kernel<false, 2, 3><<<grid, NTHREADS, Ring<3>::SMEM_TOTAL, st>>>(io, prm);

@@ -86,10 +86,11 @@ extern "C" void surs_destroy(surs_ctx *ctx)
 extern "C" const char *surs_last_error(const surs_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
 extern "C" int64_t surs_launch_count(const surs_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int64_t surs_refined_nodes(const surs_ctx *ctx) { return ctx ? ctx->refined_nodes : 0; }
-extern "C" int surs_refine_stats(const surs_ctx *ctx, int64_t *nodes, float *max_diff, float *band, int *fell_back)
+extern "C" int surs_refine_stats(const surs_ctx *ctx, int64_t *nodes, int64_t *nodes_lr_only, float *max_diff, float *band, int *fell_back)
 {
     if (!ctx) return 1;
     if (nodes) *nodes = ctx->refined_nodes;
+    if (nodes_lr_only) *nodes_lr_only = ctx->refined_lr_only;
     if (max_diff) *max_diff = ctx->refine_maxdiff;
     if (band) *band = SURS_REFINE_BAND;
     if (fell_back) *fell_back = ctx->refine_fallback;
@@ -543,24 +544,30 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
             // one pass everywhere, then split operands on the nodes the 0.5 iso-surface can depend on
             const int np = plane_hi - plane_lo;
             if (surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, np, st, 1)) return 1;
-            if (surs_ensure(ctx, (void **)&ctx->idx_list, &ctx->idx_cap, (size_t)io.n * sizeof(int64_t))) return 1;
-            int64_t nsel = 0;
+            if (surs_ensure(ctx, (void **)&ctx->idx_list, &ctx->idx_cap, 2 * (size_t)io.n * sizeof(int64_t))) return 1;
+            int64_t *idx_both = ctx->idx_list, *idx_lr = ctx->idx_list + io.n;
+            int64_t n_both = 0, n_lr = 0;
             if (surs_refine_select_impl(ctx, sdf_hr, sdf_lr, np, res[1], res[2], io.lin_base, SURS_REFINE_LEVEL, SURS_REFINE_BAND,
-                                        ctx->idx_list, &nsel, st)) return 1;
-            ctx->refined_nodes = nsel;
+                                        idx_both, idx_lr, &n_both, &n_lr, st)) return 1;
+            ctx->refined_nodes = n_both + n_lr;
+            ctx->refined_lr_only = n_lr;
             ctx->refine_maxdiff = 0.0f;
             ctx->refine_fallback = 0;
-            if (nsel == 0) return 0;
+            if (n_both + n_lr == 0) return 0;
             if (surs_col_build_table(ctx, io, res[1], plane_lo, (int64_t)np * res[1], st, 3)) return 1;
             unsigned *maxdiff = reinterpret_cast<unsigned *>(ctx->counter + 4);
             SURS_CUDA(ctx, cudaMemsetAsync(maxdiff, 0, sizeof(unsigned), st));
             PointIO part = io;
-            part.idx_list = ctx->idx_list;
-            part.n = nsel;
             part.out_hr = part.out_lr = nullptr;
             part.vol32_hr = sdf_hr; part.vol32_lr = sdf_lr; part.vol32_base = io.lin_base;
             part.refine_maxdiff = maxdiff;
-            if (surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, 3, (int64_t)plane_lo * res[1])) return 1;
+            // nodes the HR surface depends on: both MLPs; nodes only the LR surface depends on: the LR MLP alone
+            part.idx_list = idx_both;
+            part.n = n_both;
+            if (surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, 3, (int64_t)plane_lo * res[1], 2)) return 1;
+            part.idx_list = idx_lr;
+            part.n = n_lr;
+            if (surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, 3, (int64_t)plane_lo * res[1], 1)) return 1;
             // verify the band on this very input: every re-evaluated node is a sample of the one-pass error
             unsigned bits = 0;
             SURS_CUDA(ctx, cudaMemcpyAsync(&bits, maxdiff, sizeof(bits), cudaMemcpyDeviceToHost, st));
