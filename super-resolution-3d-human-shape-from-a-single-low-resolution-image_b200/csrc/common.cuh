@@ -6,7 +6,17 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/surs.h"
+
+// NVTX range around every C-ABI entry point (tracing).  Header-only NVTX v3: a no-op unless a tool
+// (nsys, ncu --nvtx) is attached.
+struct SursRange {
+    explicit SursRange(const char *name) { nvtxRangePushA(name); }
+    ~SursRange() { nvtxRangePop(); }
+};
+#define SURS_NVTX(name) SursRange surs_nvtx_range_(name)
 
 #define SURS_C_LR 256        // channels of the 'low_res' hourglass feature (lib/model/SuRSNet.py:59)
 #define SURS_C_HR 64         // channels of the 'high_res' feature            (lib/model/SuRSNet.py:61)

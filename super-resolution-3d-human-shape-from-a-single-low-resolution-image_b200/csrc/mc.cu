@@ -861,6 +861,7 @@ static int mc_count_impl(surs_ctx *ctx, const float *vol, const double *vol64, c
                          int64_t *n_verts, int64_t *n_faces, int64_t *n_ambiguous, void *stream)
 {
     if (!ctx) return 1;
+    SURS_NVTX("surs_mc_count");
     cudaStream_t st = (cudaStream_t)stream;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!vol || res[0] < 2 || res[1] < 2 || res[2] < 2) SURS_FAIL(ctx, "surs_mc_count: volume needs at least 2 nodes per axis");
@@ -972,6 +973,7 @@ extern "C" int surs_mc_emit_verts(surs_ctx *ctx, const double *mat, float *verts
                                   float *normals, float *values, int64_t vert_id_offset, int plane_offset,
                                   int32_t *seam_out, void *stream)
 {
+    SURS_NVTX("surs_mc_emit_verts");
     if (!ctx) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1009,6 +1011,7 @@ extern "C" int surs_mc_emit_verts(surs_ctx *ctx, const double *mat, float *verts
 
 extern "C" int surs_mc_emit_faces(surs_ctx *ctx, int32_t *faces, const int32_t *seam_in, void *stream)
 {
+    SURS_NVTX("surs_mc_emit_faces");
     if (!ctx) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -166,6 +166,7 @@ extern "C" int surs_set_weights(surs_ctx *ctx,
                                 const int dims_lr[SURS_NUM_LAYERS + 1], const int dims_hr[SURS_NUM_LAYERS + 1],
                                 const int *res_layers, int n_res, void *stream)
 {
+    SURS_NVTX("surs_set_weights");
     if (!ctx) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -246,6 +247,7 @@ static int ensure_feature_maps(surs_ctx *ctx, int C_lr, int H_lr, int W_lr, int 
 extern "C" int surs_set_features(surs_ctx *ctx, const float *f_lr, int C_lr, int H_lr, int W_lr,
                                  const float *f_hr, int C_hr, int H_hr, int W_hr, void *stream)
 {
+    SURS_NVTX("surs_set_features");
     if (!ctx) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -298,6 +300,7 @@ static void stripe_columns(float u_lo, float u_hi, int W, int *x0, int *x1)
 extern "C" int surs_set_features_host(surs_ctx *ctx, const float *f_lr, int C_lr, int H_lr, int W_lr,
                                       const float *f_hr, int C_hr, int H_hr, int W_hr, float u_lo, float u_hi, void *stream)
 {
+    SURS_NVTX("surs_set_features_host");
     if (!ctx) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -380,6 +383,7 @@ extern "C" int surs_set_projection(surs_ctx *ctx, int perspective, const float *
 extern "C" int surs_query(surs_ctx *ctx, const float *pts, int64_t n, const float calib[12],
                           float z_num, float z_den, int precision, float *pred_hr, float *pred_lr, void *stream)
 {
+    SURS_NVTX("surs_query");
     if (!ctx) return 1;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (check_ready(ctx, precision)) return 1;
@@ -407,6 +411,7 @@ __global__ void repack32_kernel(const float *__restrict__ src, float *__restrict
 extern "C" int surs_set_features_views(surs_ctx *ctx, int n_views, const float *f_lr, int C_lr, int H_lr, int W_lr,
                                        const float *f_hr, int C_hr, int H_hr, int W_hr, void *stream)
 {
+    SURS_NVTX("surs_set_features_views");
     if (!ctx) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -430,6 +435,7 @@ extern "C" int surs_set_features_views(surs_ctx *ctx, int n_views, const float *
 extern "C" int surs_query_views(surs_ctx *ctx, const float *pts, int64_t n, const float *calibs, float z_num, float z_den,
                                 float *pred_hr, float *pred_lr, void *stream)
 {
+    SURS_NVTX("surs_query_views");
     if (!ctx) return 1;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->have_weights) SURS_FAIL(ctx, "surs_set_weights has not been called");
@@ -499,6 +505,7 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
                               const double *transform, const float calib[12], float z_num, float z_den,
                               int precision, int plane_lo, int plane_hi, float *sdf_hr, float *sdf_lr, void *stream)
 {
+    SURS_NVTX("surs_eval_grid");
     if (!ctx) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -670,6 +677,7 @@ extern "C" int surs_eval_grid_octree(surs_ctx *ctx, const int res[3], const doub
                                      int precision, int init_resolution, double threshold,
                                      double *sdf_hr, double *sdf_lr, int64_t *n_evaluated, void *stream)
 {
+    SURS_NVTX("surs_eval_grid_octree");
     if (!ctx) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     SURS_CUDA(ctx, cudaSetDevice(ctx->device));
