@@ -725,6 +725,7 @@ struct TbParams {
     int64_t ncols;
     int64_t point0;                // >= 0: point mode -- table row r belongs to point point0 + r of io (any point source)
     int R1, plane_lo;
+    int skip_c1;                   // the C1 block is only read by query_inc.cu (opt-in SURS_COL_INC=1)
 };
 
 template <int P>
@@ -752,7 +753,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) col_table_kernel(const __grid_c
     const uint32_t tmem = bars->tmem_base;
     const int64_t ntiles = (prm.ncols + TILE_M - 1) / TILE_M;
     // the C1 block (layer 1 of the all-negative state) only serves query_inc.cu on dense grids: not computed in point mode
-    const bool skip_c1 = prm.point0 >= 0;
+    const bool skip_c1 = prm.point0 >= 0 || prm.skip_c1;
 
     if (warp < 4) {
         const int row = warp * 32 + lane;
@@ -1099,6 +1100,7 @@ int surs_col_build_table(surs_ctx *ctx, const PointIO &io, int R1, int plane_lo,
     tb.table = (float *)ctx->col_table;
     tb.ncols = ncols; tb.R1 = R1; tb.plane_lo = plane_lo;
     tb.point0 = point0;
+    tb.skip_c1 = getenv("SURS_COL_INC") == nullptr;
     const int64_t tb_tiles = (ncols + TILE_M - 1) / TILE_M;
     const int tb_grid = (int)(tb_tiles < ctx->sm_count ? tb_tiles : ctx->sm_count);
     if (passes == 3) {
