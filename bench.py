@@ -396,6 +396,11 @@ def run_ours(args):
                         "(every kernel of surs_eval_grid in this precision). It can exceed the peak because the column factoring removes 40% of "
                         "the MACs (exact refactoring, not skipped work); executed_* counts the MACs the tensor cores really ran (fp16 operands, "
                         "fp32 accumulate = the bf16 rate; refined nodes three more products each)"}
+    if world > 1:                                         # load balance of the slabs: every rank's grid-evaluation time
+        allq = torch.zeros(world, device=dev)
+        allq[rank] = q_ms
+        dist.all_reduce(allq)
+        roofline["per_rank_grid_ms"] = [round(float(v), 2) for v in allq.tolist()]
     if one_ms is not None:
         roofline["one_pass_kernel_ms"] = one_ms
         roofline["one_pass_executed_frac"] = n_slab * col_flop / (one_ms * 1e-3) / 1e12 / peak_tc
