@@ -161,23 +161,44 @@ def mesh_layout(tot_v, tot_f, want_normals=True):
     return lay, off
 
 
+def _all_ok(ok, device, group):
+    """Collective agreement: True only when every rank succeeded (so that all ranks take the same fallback)."""
+    flag = torch.tensor([1 if ok else 0], device=device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(flag.item()))
+
+
 def _peer_arenas(ctx, group, need, dst=0):
-    """Two ping-pong device arenas on rank `dst`, mapped into every rank (collective: every rank passes the same need)."""
+    """Two ping-pong device arenas on rank `dst`, mapped into every rank (collective: every rank passes the same need).
+    Returns None -- on every rank -- when CUDA IPC is not available between the ranks (the caller then gathers over NCCL)."""
     st = getattr(ctx, "_peer_arenas", None)
-    if st is not None and st["capacity"] >= need:
-        return st
+    if st is not None and (st is False or st["capacity"] >= need):
+        return st or None
     rank = dist.get_rank(group)
     if st is not None:
         for p in st["ptrs"]:
             (ctx.arena_destroy if st["owner"] else ctx.arena_close)(p)
     capacity = _align(int(need * 1.5) + (1 << 20), 1 << 20)
-    local, handles = [], [None, None]
+    local, handles, ok = [], [None, None], True
     if rank == dst:
-        local = [ctx.arena_create(capacity) for _ in range(2)]
-        handles = [h for _, h in local]
+        try:
+            local = [ctx.arena_create(capacity) for _ in range(2)]
+            handles = [h for _, h in local]
+        except RuntimeError:
+            ok = False
     box = [handles]
     dist.broadcast_object_list(box, src=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
-    ptrs = [p for p, _ in local] if rank == dst else [ctx.arena_open(h) for h in box[0]]
+    ptrs = [p for p, _ in local]
+    if rank != dst and box[0][0] is not None:
+        try:
+            ptrs = [ctx.arena_open(h) for h in box[0]]
+        except RuntimeError:
+            ok = False
+    if not _all_ok(ok and box[0][0] is not None, ctx.device, group):
+        import warnings
+        warnings.warn("surs_b200: CUDA IPC peer arenas are not available between the ranks; gathering the meshes over NCCL instead")
+        ctx._peer_arenas = False
+        return None
     st = {"capacity": capacity, "ptrs": ptrs, "owner": rank == dst, "turn": 0}
     ctx._peer_arenas = st
     return st
@@ -211,7 +232,6 @@ class HostArena:
             if int(rc) != 0:
                 raise RuntimeError("cudaHostRegister of the shared host arena failed (%s)" % rc)
         self.turn = 0
-        dist.barrier(group)
 
     def half(self):
         v = self.bytes[self.turn * self.capacity:(self.turn + 1) * self.capacity]
@@ -267,13 +287,28 @@ def read_host_arena(half, layout, tot_v, tot_f):
 
 
 def _host_arena(ctx, group, need):
+    """The shared pinned host arena of this context (collective).  None on every rank when it cannot be set up
+    (e.g. /dev/shm too small): the caller then gathers on rank 0's device and copies from there."""
     import atexit
     st = getattr(ctx, "_host_arena", None)
+    if st is False:
+        return None
     if st is not None and st.capacity >= need:
         return st
     if st is not None:
         st.close()
-    st = HostArena(ctx, group, need)
+    try:
+        st = HostArena(ctx, group, need)
+        ok = True
+    except Exception:                                  # the barrier inside HostArena may not have been reached: agree below
+        st, ok = None, False
+    if not _all_ok(ok, ctx.device, group):
+        if st is not None:
+            st.close()
+        import warnings
+        warnings.warn("surs_b200: the pinned shared-memory host arena could not be set up; gathering the meshes on rank 0 instead")
+        ctx._host_arena = False
+        return None
     ctx._host_arena = st
     atexit.register(st.close)                          # unlink the shared-memory segment when the process ends
     return st
@@ -340,8 +375,11 @@ def reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, transform
         tot_v, tot_f = allc[:, [0, 2]].sum(0), allc[:, [1, 3]].sum(0)
         layout, need = mesh_layout(tot_v, tot_f, want_normals)
         arenas = _peer_arenas(ctx, group, need)
-        base = arenas["ptrs"][arenas["turn"]]
-        arenas["turn"] ^= 1
+        if arenas is None:
+            fused = False
+        else:
+            base = arenas["ptrs"][arenas["turn"]]
+            arenas["turn"] ^= 1
     emitted, seams = [], []
     for k, c in enumerate(ctxs):
         seam_out = torch.empty((2, R1, R2), device=dev, dtype=torch.int32) if rank + 1 < world else None
@@ -440,6 +478,12 @@ def reconstruction_from_host(ctx, feat_lr_host, feat_hr_host, res, b_min, b_max,
     tot_v, tot_f = allc[:, [0, 2]].sum(0), allc[:, [1, 3]].sum(0)
     layout, need = mesh_layout(tot_v, tot_f, True)
     arena = _host_arena(ctx, group, need)
+    if arena is None:                                   # fallback: NCCL gather of what was emitted, host copy on rank 0
+        items = []
+        for k, e in enumerate(emitted):
+            items += [(e[0], allc[:, 2 * k]), (e[1], allc[:, 2 * k + 1]), (e[2], allc[:, 2 * k]), (e[3], allc[:, 2 * k])]
+        got = gather_rows_many(items, 0, group)
+        return tuple(_to_host(got)) if rank == 0 else None
     half = arena.half()
     fill_host_arena(half, layout, emitted, offs, rank)
     torch.cuda.current_stream(ctx.device).synchronize()
