@@ -1202,7 +1202,9 @@ int surs_launch_query_col_indexed(surs_ctx *ctx, const PointIO &io, int R1, int 
 int surs_launch_query_generic_x3(surs_ctx *ctx, const PointIO &io, cudaStream_t st)
 {
     if (io.n <= 0) return 0;
-    const int64_t CH = 131072;
+    // chunk = points per (table, main) kernel pair; the table takes 15.4 KB per point (512 K points: 8 GB).  Larger chunks
+    // have fewer partially filled last waves (1 CTA per SM, 128 points per tile); SURS_X3_CHUNK overrides
+    static const int64_t CH = getenv("SURS_X3_CHUNK") ? atoll(getenv("SURS_X3_CHUNK")) : 524288;
     uint8_t *base = (uint8_t *)ctx->col_weights;
     for (int64_t s0 = 0; s0 < io.n; s0 += CH) {
         const int64_t len = io.n - s0 < CH ? io.n - s0 : CH;
