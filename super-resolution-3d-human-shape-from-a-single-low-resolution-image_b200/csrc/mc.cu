@@ -81,7 +81,8 @@ __device__ __forceinline__ bool interior_test(const double (&d)[8], const uint8_
     return __dsub_rn(__dmul_rn(At, Ct), __dmul_rn(Bt, Dt)) > 0.0;
 }
 
-__device__ __forceinline__ int64_t node_lin(const McParams &p, int i, int j, int k) { return ((int64_t)i * p.R1 + j) * p.R2 + k; }
+// 32-bit node index: surs_mc_count refuses volumes with 3 * nodes >= 2^31 (the edge -> vertex-id map is indexed by 3 * node + axis)
+__device__ __forceinline__ int32_t node_lin(const McParams &p, int i, int j, int k) { return (i * p.R1 + j) * p.R2 + k; }
 
 __device__ __forceinline__ void classify_vals(const McParams &p, int i, int j, int k, const float (&val)[8], Cell &c);
 
@@ -243,15 +244,17 @@ __device__ __forceinline__ double edge_point(double base, double da, double db)
     return __ddiv_rn(__dadd_rn(__dmul_rn(base, wa), __dmul_rn(__dadd_rn(base, 1.0), wb)), __dadd_rn(wa, wb));
 }
 
-__device__ __forceinline__ double node_grad(const McParams &p, int i, int j, int k, int axis)
+// volume gradient at a node (central differences, one-sided at the border).  Normals are an API-shape obligation only
+// (the reference's caller discards them, lib/train_util.py:72) and are compared with a 1e-4 tolerance: fp32 arithmetic
+__device__ __forceinline__ float node_grad(const McParams &p, int i, int j, int k, int axis)
 {
     const int n = axis == 0 ? p.R0 : (axis == 1 ? p.R1 : p.R2);
     const int q = axis == 0 ? i : (axis == 1 ? j : k);
     const int lo = q > 0 ? q - 1 : q, hi = q < n - 1 ? q + 1 : q;
-    int il = i, jl = j, kl = k, ih = i, jh = j, kh = k;
-    if (axis == 0) { il = lo; ih = hi; } else if (axis == 1) { jl = lo; jh = hi; } else { kl = lo; kh = hi; }
-    const double dv = (double)__ldg(p.vol + node_lin(p, ih, jh, kh)) - (double)__ldg(p.vol + node_lin(p, il, jl, kl));
-    return (hi - lo) == 2 ? dv * 0.5 : dv;
+    const int stride = axis == 0 ? p.R1 * p.R2 : (axis == 1 ? p.R2 : 1);
+    const int32_t c = node_lin(p, i, j, k);
+    const float dv = __ldg(p.vol + c + (hi - q) * stride) - __ldg(p.vol + c - (q - lo) * stride);
+    return (hi - lo) == 2 ? dv * 0.5f : dv;
 }
 
 struct McOut {
@@ -266,7 +269,7 @@ struct McOut {
     int plane_offset;      // index of the volume's plane 0 along axis 0 in the full grid (slabs)
 };
 
-__device__ __forceinline__ void write_vertex(const McOut &o, int64_t v, const double pos[3], const double g[3], double value)
+__device__ __forceinline__ void write_vertex(const McOut &o, int64_t v, const double pos[3], const float g[3], double value)
 {
     const float fx = (float)pos[0], fy = (float)pos[1], fz = (float)pos[2];
     if (o.verts) { o.verts[3 * v] = fx; o.verts[3 * v + 1] = fy; o.verts[3 * v + 2] = fz; }
@@ -280,9 +283,10 @@ __device__ __forceinline__ void write_vertex(const McOut &o, int64_t v, const do
         }
     }
     if (o.normals) {
-        const double nn = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+        const float n2 = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+        const float inv = n2 > 0.0f ? rsqrtf(n2) : 0.0f;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) o.normals[3 * v + a] = nn > 0.0 ? (float)(g[a] / nn) : 0.0f;
+        for (int a = 0; a < 3; ++a) o.normals[3 * v + a] = g[a] * inv;
     }
     if (o.values) o.values[v] = (float)value;
 }
@@ -306,12 +310,12 @@ __device__ __forceinline__ void emit_edge_vertex(const McParams &p, const McOut 
     const double base = pos[axis];
     const double x = edge_point(base, dlo, dhi);
     pos[axis] = x;
-    double g[3] = {0.0, 0.0, 0.0};
+    float g[3] = {0.0f, 0.0f, 0.0f};
     if (o.normals) {
-        const double tt = x - base;
+        const float tt = (float)(x - base);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const double ga = node_grad(p, bi, bj, bk, a), gb = node_grad(p, ei, ej, ek, a);
+            const float ga = node_grad(p, bi, bj, bk, a), gb = node_grad(p, ei, ej, ek, a);
             g[a] = ga + tt * (gb - ga);
         }
     }
@@ -336,7 +340,8 @@ __device__ __forceinline__ void emit_centre_vertex(const McParams &p, const McOu
         ++n;
     }
     double pos[3] = {__ddiv_rn(s[0], (double)n), __ddiv_rn(s[1], (double)n), __ddiv_rn(s[2], (double)n)};
-    double g[3] = {0.0, 0.0, 0.0}, vmax = -INFINITY;
+    float g[3] = {0.0f, 0.0f, 0.0f};
+    double vmax = -INFINITY;
     for (int q = 0; q < 8; ++q) {
         const int ci = i + c_corner_off[3 * q], cj = j + c_corner_off[3 * q + 1], ck = k + c_corner_off[3 * q + 2];
         if (o.normals)
