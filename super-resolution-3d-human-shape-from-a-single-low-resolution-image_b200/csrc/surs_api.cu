@@ -92,7 +92,7 @@ extern "C" int surs_refine_stats(const surs_ctx *ctx, int64_t *nodes, int64_t *n
     if (nodes) *nodes = ctx->refined_nodes;
     if (nodes_lr_only) *nodes_lr_only = ctx->refined_lr_only;
     if (max_diff) *max_diff = ctx->refine_maxdiff;
-    if (band) *band = SURS_REFINE_BAND;
+    if (band) *band = ctx->refine_band > 0.0f ? ctx->refine_band : SURS_REFINE_BAND;
     if (fell_back) *fell_back = ctx->refine_fallback;
     return 0;
 }
@@ -554,7 +554,10 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
             if (surs_ensure(ctx, (void **)&ctx->idx_list, &ctx->idx_cap, 2 * (size_t)io.n * sizeof(int64_t))) return 1;
             int64_t *idx_both = ctx->idx_list, *idx_lr = ctx->idx_list + io.n;
             int64_t n_both = 0, n_lr = 0;
-            if (surs_refine_select_impl(ctx, sdf_hr, sdf_lr, np, res[1], res[2], io.lin_base, SURS_REFINE_LEVEL, SURS_REFINE_BAND,
+            // (SURS_REFINE_BAND overrides the band: the tests use a tiny one to drive the fall-back below)
+            const float band = getenv("SURS_REFINE_BAND") ? (float)atof(getenv("SURS_REFINE_BAND")) : SURS_REFINE_BAND;
+            ctx->refine_band = band;
+            if (surs_refine_select_impl(ctx, sdf_hr, sdf_lr, np, res[1], res[2], io.lin_base, SURS_REFINE_LEVEL, band,
                                         idx_both, idx_lr, &n_both, &n_lr, st)) return 1;
             ctx->refined_nodes = n_both + n_lr;
             ctx->refined_lr_only = n_lr;
@@ -580,14 +583,14 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
             SURS_CUDA(ctx, cudaMemcpyAsync(&bits, maxdiff, sizeof(bits), cudaMemcpyDeviceToHost, st));
             SURS_CUDA(ctx, cudaStreamSynchronize(st));
             memcpy(&ctx->refine_maxdiff, &bits, sizeof(float));
-            if (!(ctx->refine_maxdiff < SURS_REFINE_SAFETY * SURS_REFINE_BAND)) {
+            if (!(ctx->refine_maxdiff < SURS_REFINE_SAFETY * band)) {
                 ctx->refine_fallback = 1;
                 static bool warned = false;
                 if (!warned) {
                     warned = true;
                     fprintf(stderr, "libsurs: SURS_PREC_FP16R band check failed (max |one-pass - split| = %g >= %g): "
                                     "re-evaluating the slab with split operands (SURS_PREC_FP16X3)\n",
-                            ctx->refine_maxdiff, SURS_REFINE_SAFETY * SURS_REFINE_BAND);
+                            ctx->refine_maxdiff, SURS_REFINE_SAFETY * band);
                 }
                 return surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, np, st, 3);
             }
