@@ -65,6 +65,48 @@ __global__ void __launch_bounds__(SEL_THREADS) octree_select_kernel(uint8_t *__r
     }
 }
 
+// select at the finest level (reso = 1: every node is a candidate) for volumes whose node count is a multiple of 4:
+// one 32-bit load brings a thread's four consecutive dirty flags (the per-candidate byte loads of the generic kernel
+// reach a fraction of the memory bandwidth), the list stays in ascending node order
+__global__ void __launch_bounds__(SEL_THREADS) octree_select1_kernel(uint8_t *__restrict__ dirty, int64_t *__restrict__ idx,
+                                                                     unsigned long long *counter, int64_t nquads)
+{
+    __shared__ unsigned warp_cnt[SEL_THREADS / 32];
+    __shared__ unsigned long long block_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * SEL_THREADS + threadIdx.x;
+    uint32_t flags = 0;
+    if (q < nquads) flags = reinterpret_cast<const uint32_t *>(dirty)[q];
+    unsigned take = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) take |= (((flags >> (8 * b)) & 0xffu) == 1u) ? (1u << b) : 0u;
+    const unsigned mine = __popc(take);
+    unsigned inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += x;
+    }
+    if (lane == 31) warp_cnt[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int w = 0; w < SEL_THREADS / 32; ++w) { unsigned c = warp_cnt[w]; warp_cnt[w] = tot; tot += c; }
+        block_base = tot ? atomicAdd(counter, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (!take) return;
+    unsigned long long o = block_base + warp_cnt[warp] + inc - mine;
+    uint32_t cleared = flags;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        if ((take >> b) & 1u) {
+            idx[o++] = 4 * q + b;
+            cleared &= ~(0xffu << (8 * b));                            // lib/sdf.py:77: dirty[test] = False
+        }
+    reinterpret_cast<uint32_t *>(dirty)[q] = cleared;
+}
+
 // SURS_PREC_FP16R: nodes of a dense slab [np, R1, R2] whose one-pass value must be recomputed with split operands --
 // every node that marching cubes at `level` can interpolate from after the refinement: the node or one of its six
 // neighbours lies within `band` of the level (its inside / outside bit may still change), or its bit differs from a
@@ -201,6 +243,42 @@ __global__ void octree_fill_kernel(double *__restrict__ hr, double *__restrict__
     dirty[lin] = 0;
 }
 
+// pass B, R2 % 4 == 0 and reso = 2 or a multiple of 4: one thread per FOUR consecutive nodes of a row (two cells for reso = 2, one cell
+// for reso >= 4): a quarter of the threads, one centre-flag read per cell instead of per node, 32-byte stores
+__global__ void __launch_bounds__(128) octree_fill4_kernel(double *__restrict__ hr, double *__restrict__ lr, uint8_t *__restrict__ dirty,
+                                                           int R0, int R1, int R2, int m0, int m1, int m2, int reso)
+{
+    const int k0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int j = blockIdx.y, i = blockIdx.z;
+    if (k0 >= R2) return;
+    const int cx = i / reso, cy = j / reso;
+    if (cx >= m0 || cy >= m1) return;
+    const int h = reso / 2;
+    const int64_t row = ((int64_t)i * R1 + j) * R2;
+    const int64_t crow = ((int64_t)(cx * reso + h) * R1 + (cy * reso + h)) * R2;
+    const int ncell = reso >= 4 ? 1 : 2;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (c >= ncell) break;
+        const int k = k0 + 2 * c, cz = k / reso;                     // reso = 2: nodes (k0, k0+1) and (k0+2, k0+3); else all four
+        if (cz >= m2) continue;
+        const int64_t centre = crow + (cz * reso + h);
+        const unsigned code = dirty[centre];
+        if (code < 2) continue;
+        const int n = reso >= 4 ? 4 : 2;
+        const double vh = (code & 2) ? hr[centre] : 0.0, vl = (code & 4) ? lr[centre] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q >= n) break;
+            const int64_t lin = row + k + q;
+            if (lin == centre) continue;                             // holds the value and the code
+            if (code & 2) hr[lin] = vh;
+            if (code & 4) lr[lin] = vl;
+            dirty[lin] = 0;
+        }
+    }
+}
+
 }  // namespace
 
 int surs_octree_select_impl(surs_ctx *ctx, const int res[3], int reso, uint8_t *dirty, int64_t *idx,
@@ -210,9 +288,14 @@ int surs_octree_select_impl(surs_ctx *ctx, const int res[3], int reso, uint8_t *
     const int n0 = (res[0] + reso - 1) / reso, n1 = (res[1] + reso - 1) / reso, n2 = (res[2] + reso - 1) / reso;
     const int64_t ncand = (int64_t)n0 * n1 * n2;
     SURS_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned long long), st));
-    const int64_t per_block = SEL_THREADS * SEL_PER_THREAD;
-    const int64_t blocks = (ncand + per_block - 1) / per_block;
-    octree_select_kernel<<<(unsigned)blocks, SEL_THREADS, 0, st>>>(dirty, idx, ctx->counter, res[1], res[2], n1, n2, ncand, reso);
+    if (reso == 1 && ncand % 4 == 0 && ((uintptr_t)dirty & 3) == 0) {
+        const int64_t nquads = ncand / 4;
+        octree_select1_kernel<<<(unsigned)((nquads + SEL_THREADS - 1) / SEL_THREADS), SEL_THREADS, 0, st>>>(dirty, idx, ctx->counter, nquads);
+    } else {
+        const int64_t per_block = SEL_THREADS * SEL_PER_THREAD;
+        const int64_t blocks = (ncand + per_block - 1) / per_block;
+        octree_select_kernel<<<(unsigned)blocks, SEL_THREADS, 0, st>>>(dirty, idx, ctx->counter, res[1], res[2], n1, n2, ncand, reso);
+    }
     SURS_LAUNCH_CHECK(ctx, "octree_select_kernel");
     unsigned long long n = 0;
     SURS_CUDA(ctx, cudaMemcpyAsync(&n, ctx->counter, sizeof(n), cudaMemcpyDeviceToHost, st));
@@ -251,8 +334,13 @@ int surs_octree_cells_impl(surs_ctx *ctx, const int res[3], int reso, double thr
                                                                          m[1], m[2], ncell, reso, threshold, ctx->counter + 16);
     SURS_LAUNCH_CHECK(ctx, "octree_decide_kernel");
     if (res[1] > 65535 || res[0] > 65535) SURS_FAIL(ctx, "octree: resolution too large");
-    dim3 grid((res[2] + 127) / 128, res[1], res[0]);
-    octree_fill_kernel<<<grid, 128, 0, st>>>(sdf_hr, sdf_lr, dirty, res[0], res[1], res[2], m[0], m[1], m[2], reso);
+    if (res[2] % 4 == 0 && (reso == 2 || reso % 4 == 0)) {
+        dim3 grid((res[2] / 4 + 127) / 128, res[1], res[0]);
+        octree_fill4_kernel<<<grid, 128, 0, st>>>(sdf_hr, sdf_lr, dirty, res[0], res[1], res[2], m[0], m[1], m[2], reso);
+    } else {
+        dim3 grid((res[2] + 127) / 128, res[1], res[0]);
+        octree_fill_kernel<<<grid, 128, 0, st>>>(sdf_hr, sdf_lr, dirty, res[0], res[1], res[2], m[0], m[1], m[2], reso);
+    }
     SURS_LAUNCH_CHECK(ctx, "octree_fill_kernel");
     return 0;
 }
