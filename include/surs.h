@@ -56,9 +56,11 @@ int surs_version(void);
 int64_t surs_refined_nodes(const surs_ctx *ctx);
 /* ... how many of them only the LR surface depends on (those go through the LR MLP alone; the HR MLP needs the LR
  * prediction as an input, so nodes of the HR surface take both), and the run-time check of the band: max |one-pass -
- * split| over the re-evaluated values, the band, and whether the check failed (max_diff >= 0.8 band), in which case the
- * whole slab was re-evaluated with SURS_PREC_FP16X3.  Any pointer may be NULL. */
-int surs_refine_stats(const surs_ctx *ctx, int64_t *nodes, int64_t *nodes_lr_only, float *max_diff, float *band, int *fell_back);
+ * split| over the re-evaluated values and the band.  When the maximum is not below 0.8 band the band is widened once
+ * (to max_diff / 0.6; `attempts` = 2) and the selection repeated; if the check still fails the whole slab is
+ * re-evaluated with SURS_PREC_FP16X3 (`fell_back`).  Any pointer may be NULL. */
+int surs_refine_stats(const surs_ctx *ctx, int64_t *nodes, int64_t *nodes_lr_only, float *max_diff, float *band, int *fell_back,
+                      int *attempts);
 
 /* Lifetime.  `device` is a CUDA ordinal. */
 int surs_create(surs_ctx **out, int device);

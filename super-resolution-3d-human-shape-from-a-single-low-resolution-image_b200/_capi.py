@@ -33,7 +33,7 @@ _lib = None
 SIGNATURES = {
     "surs_version": (ctypes.c_int, []),
     "surs_refined_nodes": (_I64, [_P]),
-    "surs_refine_stats": (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
+    "surs_refine_stats": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "surs_mc_seam_violations": (_I64, [_P]),
     "surs_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_int]),
     "surs_destroy": (None, [_P]),
@@ -229,10 +229,10 @@ class Context:
     def refine_stats(self):
         """Run-time band check of the last eval_grid(precision=PREC_FP16R): nodes re-evaluated, max |one-pass - split|
         over them, the band, and whether the check failed (-> the slab was re-evaluated with PREC_FP16X3)."""
-        n, nl, d, b, f = _I64(0), _I64(0), ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int(0)
-        self.lib.surs_refine_stats(self._h, ctypes.byref(n), ctypes.byref(nl), ctypes.byref(d), ctypes.byref(b), ctypes.byref(f))
+        n, nl, d, b, f, a = _I64(0), _I64(0), ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int(0), ctypes.c_int(0)
+        self.lib.surs_refine_stats(self._h, ctypes.byref(n), ctypes.byref(nl), ctypes.byref(d), ctypes.byref(b), ctypes.byref(f), ctypes.byref(a))
         return {"nodes": int(n.value), "nodes_lr_mlp_only": int(nl.value), "max_diff": float(d.value), "band": float(b.value),
-                "fell_back": bool(f.value)}
+                "fell_back": bool(f.value), "attempts": int(a.value)}
 
     def mc_interior_stats(self):
         """(cells with an interior ambiguity, cells that took the tunnel triangulation) of the last mc_count."""

@@ -182,6 +182,7 @@ struct surs_ctx {
     int64_t refined_lr_only;               // ... of which only the LR surface depends on (LR MLP alone)
     float refine_band;                     // ... the band it used
     float refine_maxdiff;                  // ... max |one-pass - split| over them
+    int refine_attempts;                   // ... selections it took (> 1: the band had to be widened)
     int refine_fallback;                   // ... 1: the band check failed and the whole slab was re-evaluated with split operands
     void *mc_count_stream;                 // stream of the last surs_mc_count (surs_mc_interior_stats)
     void *mc_faces_stream;                 // stream of the last surs_mc_emit_faces (surs_mc_seam_violations reads its counter)

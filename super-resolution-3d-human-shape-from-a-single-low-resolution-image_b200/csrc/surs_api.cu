@@ -86,8 +86,10 @@ extern "C" void surs_destroy(surs_ctx *ctx)
 extern "C" const char *surs_last_error(const surs_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
 extern "C" int64_t surs_launch_count(const surs_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int64_t surs_refined_nodes(const surs_ctx *ctx) { return ctx ? ctx->refined_nodes : 0; }
-extern "C" int surs_refine_stats(const surs_ctx *ctx, int64_t *nodes, int64_t *nodes_lr_only, float *max_diff, float *band, int *fell_back)
+extern "C" int surs_refine_stats(const surs_ctx *ctx, int64_t *nodes, int64_t *nodes_lr_only, float *max_diff, float *band, int *fell_back,
+                                 int *attempts)
 {
+    if (ctx && attempts) *attempts = ctx->refine_attempts;
     if (!ctx) return 1;
     if (nodes) *nodes = ctx->refined_nodes;
     if (nodes_lr_only) *nodes_lr_only = ctx->refined_lr_only;
@@ -553,48 +555,65 @@ extern "C" int surs_eval_grid(surs_ctx *ctx, const int res[3], const double b_mi
             if (surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, np, st, 1)) return 1;
             if (surs_ensure(ctx, (void **)&ctx->idx_list, &ctx->idx_cap, 2 * (size_t)io.n * sizeof(int64_t))) return 1;
             int64_t *idx_both = ctx->idx_list, *idx_lr = ctx->idx_list + io.n;
-            int64_t n_both = 0, n_lr = 0;
-            // (SURS_REFINE_BAND overrides the band: the tests use a tiny one to drive the fall-back below)
-            const float band = getenv("SURS_REFINE_BAND") ? (float)atof(getenv("SURS_REFINE_BAND")) : SURS_REFINE_BAND;
-            ctx->refine_band = band;
-            if (surs_refine_select_impl(ctx, sdf_hr, sdf_lr, np, res[1], res[2], io.lin_base, SURS_REFINE_LEVEL, band,
-                                        idx_both, idx_lr, &n_both, &n_lr, st)) return 1;
-            ctx->refined_nodes = n_both + n_lr;
-            ctx->refined_lr_only = n_lr;
-            ctx->refine_maxdiff = 0.0f;
-            ctx->refine_fallback = 0;
-            if (n_both + n_lr == 0) return 0;
-            if (surs_col_build_table(ctx, io, res[1], plane_lo, (int64_t)np * res[1], st, 3)) return 1;
+            // (SURS_REFINE_BAND overrides the band, SURS_REFINE_RETRIES the number of widened retries: the tests use a tiny
+            // band to drive the retry and the fall-back below)
+            float band = getenv("SURS_REFINE_BAND") ? (float)atof(getenv("SURS_REFINE_BAND")) : SURS_REFINE_BAND;
+            const int retries = getenv("SURS_REFINE_RETRIES") ? atoi(getenv("SURS_REFINE_RETRIES")) : 1;
             unsigned *maxdiff = reinterpret_cast<unsigned *>(ctx->counter + 4);
             SURS_CUDA(ctx, cudaMemsetAsync(maxdiff, 0, sizeof(unsigned), st));
-            PointIO part = io;
-            part.out_hr = part.out_lr = nullptr;
-            part.vol32_hr = sdf_hr; part.vol32_lr = sdf_lr; part.vol32_base = io.lin_base;
-            part.refine_maxdiff = maxdiff;
-            // nodes the HR surface depends on: both MLPs; nodes only the LR surface depends on: the LR MLP alone
-            part.idx_list = idx_both;
-            part.n = n_both;
-            if (surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, 3, (int64_t)plane_lo * res[1], 2)) return 1;
-            part.idx_list = idx_lr;
-            part.n = n_lr;
-            if (surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, 3, (int64_t)plane_lo * res[1], 1)) return 1;
-            // verify the band on this very input: every re-evaluated node is a sample of the one-pass error
-            unsigned bits = 0;
-            SURS_CUDA(ctx, cudaMemcpyAsync(&bits, maxdiff, sizeof(bits), cudaMemcpyDeviceToHost, st));
-            SURS_CUDA(ctx, cudaStreamSynchronize(st));
-            memcpy(&ctx->refine_maxdiff, &bits, sizeof(float));
-            if (!(ctx->refine_maxdiff < SURS_REFINE_SAFETY * band)) {
-                ctx->refine_fallback = 1;
+            ctx->refined_nodes = ctx->refined_lr_only = 0;
+            ctx->refine_maxdiff = 0.0f;
+            ctx->refine_fallback = 0;
+            ctx->refine_attempts = 0;
+            bool have_table = false;
+            for (int attempt = 0;; ++attempt) {
+                int64_t n_both = 0, n_lr = 0;
+                ctx->refine_band = band;
+                ctx->refine_attempts = attempt + 1;
+                if (surs_refine_select_impl(ctx, sdf_hr, sdf_lr, np, res[1], res[2], io.lin_base, SURS_REFINE_LEVEL, band,
+                                            idx_both, idx_lr, &n_both, &n_lr, st)) return 1;
+                ctx->refined_nodes = n_both + n_lr;          // the last (widest) selection; earlier ones are subsets up to noise
+                ctx->refined_lr_only = n_lr;
+                if (n_both + n_lr == 0) return 0;
+                if (!have_table && surs_col_build_table(ctx, io, res[1], plane_lo, (int64_t)np * res[1], st, 3)) return 1;
+                have_table = true;
+                PointIO part = io;
+                part.out_hr = part.out_lr = nullptr;
+                part.vol32_hr = sdf_hr; part.vol32_lr = sdf_lr; part.vol32_base = io.lin_base;
+                part.refine_maxdiff = maxdiff;
+                // nodes the HR surface depends on: both MLPs; nodes only the LR surface depends on: the LR MLP alone
+                part.idx_list = idx_both;
+                part.n = n_both;
+                if (surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, 3, (int64_t)plane_lo * res[1], 2)) return 1;
+                part.idx_list = idx_lr;
+                part.n = n_lr;
+                if (surs_launch_query_col_indexed(ctx, part, res[1], res[2], st, 3, (int64_t)plane_lo * res[1], 1)) return 1;
+                // verify the band on this very input: every re-evaluated value is a sample of the one-pass error (the
+                // maximum runs over all attempts; values refined before compare equal to themselves)
+                unsigned bits = 0;
+                SURS_CUDA(ctx, cudaMemcpyAsync(&bits, maxdiff, sizeof(bits), cudaMemcpyDeviceToHost, st));
+                SURS_CUDA(ctx, cudaStreamSynchronize(st));
+                memcpy(&ctx->refine_maxdiff, &bits, sizeof(float));
+                if (ctx->refine_maxdiff < SURS_REFINE_SAFETY * band) return 0;
                 static bool warned = false;
-                if (!warned) {
+                if (attempt < retries && ctx->refine_maxdiff < 0.15f) {
+                    // the one-pass error on this input is larger than the band assumed: widen the band so that the measured
+                    // maximum sits at 0.6 of it and select again (what was refined already is re-evaluated to the same value)
+                    if (!warned)
+                        fprintf(stderr, "libsurs: SURS_PREC_FP16R band %g too narrow for this input (max |one-pass - split| = %g): retrying with %g\n",
+                                band, ctx->refine_maxdiff, ctx->refine_maxdiff / 0.6f);
                     warned = true;
+                    band = ctx->refine_maxdiff / 0.6f;
+                    continue;
+                }
+                ctx->refine_fallback = 1;
+                if (!warned)
                     fprintf(stderr, "libsurs: SURS_PREC_FP16R band check failed (max |one-pass - split| = %g >= %g): "
                                     "re-evaluating the slab with split operands (SURS_PREC_FP16X3)\n",
                             ctx->refine_maxdiff, SURS_REFINE_SAFETY * band);
-                }
+                warned = true;
                 return surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, np, st, 3);
             }
-            return 0;
         }
         return col_inc ? surs_launch_query_inc(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st)
                        : surs_launch_query_col(ctx, io, res[1], res[2], plane_lo, plane_hi - plane_lo, st);
