@@ -514,6 +514,29 @@ def test_refined_mode_widens_the_band_or_falls_back_when_the_check_fails(ctx, ca
     assert not st["fell_back"] and st["attempts"] == 1 and 0 < st["nodes_lr_mlp_only"] < st["nodes"]
 
 
+@pytest.mark.parametrize("seed,gain", [(3, 6.0), (4, 7.5), (5, 3.0), (6, 8.5)])
+def test_default_precision_meets_the_tolerance_on_other_weights(seed, gain):
+    """THE tolerance for the default precision must not depend on the one synthetic checkpoint the band was measured
+    on: sharper (gain 7.5, 8.5: logits of +-60) and flatter (gain 3) MLPs, other features -- whatever the run-time band check decides
+    (first band, widened band, or split operands everywhere), every value marching cubes reads is within 1e-3 of the
+    fp32 mode and no inside / outside bit outside the 1e-3 band differs."""
+    from surs_b200 import _capi
+    c = _capi.Context("cuda:0")
+    try:
+        case = syn.SyntheticCase(S=64, seed=seed, gain=gain)
+        load_case(c, case)
+        args = ((64, 48, 128), [-0.5] * 3, [0.5, 0.25, 0.5], case.calib) + znum(case)
+        got = c.eval_grid(*args)                                  # default precision
+        st = c.refine_stats
+        ref = c.eval_grid(*args, precision=_capi.PREC_FP32)
+        one = c.eval_grid(*args, precision=_capi.PREC_FP16)
+        print("seed %d gain %g: one-pass max err %.3g; refinement %s" % (seed, gain, max(float((one[0] - ref[0]).abs().max()), float((one[1] - ref[1]).abs().max())), st))
+        for g, r, name in ((got[0], ref[0], "HR"), (got[1], ref[1], "LR")):
+            helpers.parity_report(g, r, mask=helpers.mc_read_mask(r > 0.5), label="default precision, seed %d gain %g, %s" % (seed, gain, name))
+    finally:
+        c.close()
+
+
 def test_feature_stripe_upload_for_slabs(ctx, case32):
     """surs_set_features_host with a u range uploads only the pixel columns a slab samples: the slab is bit-identical
     to the one computed from whole maps, and calls that would sample outside the stripe are refused."""
