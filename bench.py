@@ -359,7 +359,7 @@ def run_ours(args):
     del out
 
     # ---- dominant kernel: the fused query of the slab, timed alone with CUDA events on its stream -------------------
-    lo, hi = parallel.slab_ranges(res, world)[rank]
+    lo, hi = (parallel.current_slab_ranges(ctx, res, world) if world > 1 else parallel.slab_ranges(res, world))[rank]
     hi_h = min(hi + 1, res)
     n_slab = (hi_h - lo) * res * res
 
@@ -401,6 +401,9 @@ def run_ours(args):
         allq[rank] = q_ms
         dist.all_reduce(allq)
         roofline["per_rank_grid_ms"] = [round(float(v), 2) for v in allq.tolist()]
+        roofline["slab_planes"] = [hi_ - lo_ for lo_, hi_ in parallel.current_slab_ranges(ctx, res, world)]
+        roofline["slab_balance"] = ("adaptive: slab sizes follow the per-rank grid-evaluation times of the previous step (SURS_BALANCE=0: equal slabs); "
+                                    "the gathered mesh is identical for any partition (mesh.matches_single_gpu)")
     if one_ms is not None:
         roofline["one_pass_kernel_ms"] = one_ms
         roofline["one_pass_executed_frac"] = n_slab * col_flop / (one_ms * 1e-3) / 1e12 / peak_tc

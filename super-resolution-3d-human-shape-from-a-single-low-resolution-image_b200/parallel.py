@@ -46,6 +46,55 @@ def slab_ranges(n_planes, world):
     return out
 
 
+def weighted_slab_ranges(n_planes, shares):
+    """Contiguous plane ranges whose CELL counts follow `shares` (one positive weight per rank) as closely as integer
+    counts allow; every rank keeps at least one cell layer; the last rank keeps the final plane (as slab_ranges)."""
+    world = len(shares)
+    cells = n_planes - 1
+    w = np.maximum(np.asarray(shares, dtype=np.float64), 1e-9)
+    ideal = np.cumsum(w) / w.sum() * cells
+    cuts = [0]
+    for r in range(world - 1):
+        lo_allowed, hi_allowed = cuts[-1] + 1, cells - (world - 1 - r)
+        cuts.append(int(min(max(int(round(ideal[r])), lo_allowed), hi_allowed)))
+    cuts.append(cells)
+    out = [(cuts[r], cuts[r + 1]) for r in range(world)]
+    out[-1] = (out[-1][0], n_planes)
+    return out
+
+
+def current_slab_ranges(ctx, n_planes, world):
+    """The partition the next reconstruct_slab of this context will use: equal slabs, or -- after the first step and
+    unless SURS_BALANCE=0 -- slabs sized by the per-rank grid-evaluation times measured in the previous step."""
+    st = getattr(ctx, "_balance", None)
+    if st is None or st["n_planes"] != n_planes or st["world"] != world or os.environ.get("SURS_BALANCE") == "0":
+        return slab_ranges(n_planes, world)
+    return weighted_slab_ranges(n_planes, st["shares"])
+
+
+BALANCE_STEPS = 3      # calibration steps after which the partition is frozen (changing slab sizes re-allocates scratch)
+
+
+def _update_balance(ctx, n_planes, world, ranges, times_us):
+    """New shares from the measured per-rank times: a rank's speed is (cells it had) / (time it took); the next
+    partition gives every rank cells in proportion to its speed (damped by one half, so that noise does not make the
+    cuts oscillate).  Every rank calls this with the same all-gathered numbers, hence computes the same partition.
+    Only the first BALANCE_STEPS steps of a (resolution, world size) calibrate; then the partition stays fixed, so that
+    the slabs' scratch buffers and output tensors keep their sizes."""
+    st = getattr(ctx, "_balance", None)
+    if st is not None and st["n_planes"] == n_planes and st["world"] == world and st["updates"] >= BALANCE_STEPS:
+        return
+    updates = st["updates"] + 1 if (st is not None and st["n_planes"] == n_planes and st["world"] == world) else 1
+    t = np.maximum(np.asarray(times_us, dtype=np.float64), 1.0)
+    had = np.array([hi - lo for lo, hi in ranges], dtype=np.float64)
+    had[-1] -= 1.0                                       # the last rank's range includes the final plane, not a cell layer
+    speed = np.maximum(had, 1.0) / t
+    target = speed / speed.sum()
+    old = had / had.sum()
+    shares = 0.5 * old + 0.5 * target
+    ctx._balance = {"n_planes": n_planes, "world": world, "shares": shares, "times_us": [float(v) for v in t], "updates": updates}
+
+
 def slab_u_range(res, b_min, b_max, calib, plane_lo, plane_hi):
     """Range of the image coordinate u = (calib . [x, y, z, 1])[0] (lib/geometry.py:15-31) over the grid nodes of
     planes [plane_lo, plane_hi): the extremes of an affine map over a box are at its corners."""
@@ -335,10 +384,16 @@ def reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, transform
     rank = dist.get_rank(group) if distributed else 0
     world = dist.get_world_size(group) if distributed else 1
     R0, R1, R2 = (int(v) for v in res)
-    lo, hi = slab_ranges(R0, world)[rank]
+    ranges = current_slab_ranges(ctx, R0, world) if distributed else slab_ranges(R0, world)
+    lo, hi = ranges[rank]
     hi_halo = min(hi + 1, R0)
+    ev0, ev1 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if distributed else (None, None)
+    if distributed:
+        ev0.record()
     vols = ctx.eval_grid(res, b_min, b_max, calib, z_num, z_den, transform=transform, precision=precision,
                          plane_lo=lo, plane_hi=hi_halo)
+    if distributed:
+        ev1.record()
     flags = _capi.MC_LOWER_FOREIGN if rank > 0 else 0
     dev = ctx.device
     ctxs = _mc_contexts(ctx) if distributed else (ctx, ctx)
@@ -362,10 +417,15 @@ def reconstruct_slab(ctx, res, b_min, b_max, calib, z_num, z_den, mat, transform
         return tuple(results)
     counts = [c.mc_count(vol, MC_LEVEL, flags)[:2] for c, vol in zip(ctxs, vols)]
     tick("mc_count x2")
-    mine = torch.tensor([counts[0][0], counts[0][1], counts[1][0], counts[1][1]], device=dev, dtype=torch.int64)
-    allc = torch.empty((world, 4), device=dev, dtype=torch.int64)
+    # the counts travel together with this rank's grid-evaluation time (its events are complete: mc_count synchronised),
+    # from which every rank derives the same partition for the NEXT step (adaptive slab balance, current_slab_ranges)
+    grid_us = int(ev0.elapsed_time(ev1) * 1e3)
+    mine = torch.tensor([counts[0][0], counts[0][1], counts[1][0], counts[1][1], grid_us], device=dev, dtype=torch.int64)
+    allc = torch.empty((world, 5), device=dev, dtype=torch.int64)
     dist.all_gather_into_tensor(allc, mine, group=group)
     allc = allc.cpu().numpy()
+    _update_balance(ctx, R0, world, ranges, allc[:, 4])
+    allc = np.ascontiguousarray(allc[:, :4])
     offs = exclusive_offsets(allc)
     tick("all-gather of the counts")
     # gather == True: emit straight into rank 0's arena through the NVLink peer mapping (no payload collective)
@@ -466,7 +526,7 @@ def reconstruction_from_host(ctx, feat_lr_host, feat_hr_host, res, b_min, b_max,
     rank = dist.get_rank(group) if distributed else 0
     world = dist.get_world_size(group) if distributed else 1
     # this rank only samples the image coordinates u of its slab (+ halo plane): upload that stripe of pixel columns
-    lo, hi = slab_ranges(int(res[0]), world)[rank]
+    lo, hi = (current_slab_ranges(ctx, int(res[0]), world) if distributed else slab_ranges(int(res[0]), world))[rank]
     hi = min(hi + 1, int(res[0]))
     ctx.set_features_host(feat_lr_host, feat_hr_host, u_range=slab_u_range(res, b_min, b_max, calib, lo, hi))
     if not distributed or os.environ.get("SURS_NCCL_GATHER") is not None:

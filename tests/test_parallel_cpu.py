@@ -154,3 +154,33 @@ def test_shared_host_arena_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_weighted_slab_ranges_and_balance_update():
+    class Ctx:
+        pass
+    ctx = Ctx()
+    for planes, world in ((512, 8), (96, 3), (9, 4)):
+        eq = parallel.slab_ranges(planes, world)
+        assert parallel.current_slab_ranges(ctx, planes, world) == eq
+        w = parallel.weighted_slab_ranges(planes, [1.0] * world)           # equal weights: the equal partition up to rounding
+        assert all(abs(a[0] - b[0]) <= 1 and abs(a[1] - b[1]) <= 1 for a, b in zip(w, eq)) and w[0][0] == 0 and w[-1][1] == planes
+    # rank 2 is 20 % slower: after a few updates it holds fewer cells, all cells are still covered exactly once
+    planes, world = 512, 4
+    ranges = parallel.slab_ranges(planes, world)
+    frozen = None
+    for it in range(6):
+        if it == parallel.BALANCE_STEPS:
+            frozen = ranges                                        # calibration is over: the partition no longer moves
+        cells = [hi - lo - (1 if r == world - 1 else 0) for r, (lo, hi) in enumerate(ranges)]
+        times = [c * (1.2 if r == 2 else 1.0) * 400 for r, c in enumerate(cells)]
+        parallel._update_balance(ctx, planes, world, ranges, times)
+        ranges = parallel.current_slab_ranges(ctx, planes, world)
+        assert ranges[0][0] == 0 and ranges[-1][1] == planes and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert all(hi - lo >= 1 for lo, hi in ranges)
+    assert ranges == frozen
+    cells = [hi - lo - (1 if r == world - 1 else 0) for r, (lo, hi) in enumerate(ranges)]
+    assert cells[2] < cells[0] and abs(cells[2] * 1.2 - cells[0]) <= 6.0 and sum(cells) == planes - 1
+    # extreme weights still leave every rank a cell layer
+    r = parallel.weighted_slab_ranges(9, [1000.0, 1.0, 1.0, 1.0])
+    assert [hi - lo for lo, hi in r] == [5, 1, 1, 2] and r[-1][1] == 9
