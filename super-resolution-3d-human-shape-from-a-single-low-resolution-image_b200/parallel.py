@@ -82,9 +82,16 @@ def _update_balance(ctx, n_planes, world, ranges, times_us):
     Only the first BALANCE_STEPS steps of a (resolution, world size) calibrate; then the partition stays fixed, so that
     the slabs' scratch buffers and output tensors keep their sizes."""
     st = getattr(ctx, "_balance", None)
-    if st is not None and st["n_planes"] == n_planes and st["world"] == world and st["updates"] >= BALANCE_STEPS:
+    same = st is not None and st["n_planes"] == n_planes and st["world"] == world
+    if not same:
+        # the very first step of a configuration pays one-off allocations: it only opens the calibration
+        had0 = np.array([hi - lo for lo, hi in ranges], dtype=np.float64)
+        had0[-1] -= 1.0
+        ctx._balance = {"n_planes": n_planes, "world": world, "shares": had0 / had0.sum(), "times_us": None, "updates": 0}
         return
-    updates = st["updates"] + 1 if (st is not None and st["n_planes"] == n_planes and st["world"] == world) else 1
+    if st["updates"] >= BALANCE_STEPS:
+        return
+    updates = st["updates"] + 1
     t = np.maximum(np.asarray(times_us, dtype=np.float64), 1.0)
     had = np.array([hi - lo for lo, hi in ranges], dtype=np.float64)
     had[-1] -= 1.0                                       # the last rank's range includes the final plane, not a cell layer

@@ -169,8 +169,8 @@ def test_weighted_slab_ranges_and_balance_update():
     planes, world = 512, 4
     ranges = parallel.slab_ranges(planes, world)
     frozen = None
-    for it in range(6):
-        if it == parallel.BALANCE_STEPS:
+    for it in range(7):
+        if it == parallel.BALANCE_STEPS + 1:                       # (the first step only opens the calibration)
             frozen = ranges                                        # calibration is over: the partition no longer moves
         cells = [hi - lo - (1 if r == world - 1 else 0) for r, (lo, hi) in enumerate(ranges)]
         times = [c * (1.2 if r == 2 else 1.0) * 400 for r, c in enumerate(cells)]
