@@ -51,7 +51,7 @@ template <int P> struct Ring {
     static constexpr int SMEM_CV = SMEM_A + NA_SLOT * A_BLK_BYTES;
     static constexpr int SMEM_GV = SMEM_CV + 2 * CV_BYTES;
     static constexpr int SMEM_BAR = SMEM_GV + GV_BYTES;
-    static constexpr int SMEM_PREDX = SMEM_BAR + 256;   // pred_lr hand-over between the two warps of a quarter
+    static constexpr int SMEM_PREDX = SMEM_BAR + 256;   // layer-4 partial sums and pred_lr hand-over between the warps
     static constexpr int SMEM_TOTAL = SMEM_PREDX + 512 + 1024;
     static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 };
@@ -436,32 +436,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                 if (m == 0) epilogue_256<P, true, false>(e, lane_l2, ID_L2, cvm + CV_C2, gvm + GV_WZ2, nullptr);
                 else epilogue_256<P, true, true>(e, lane_l2, ID_L2, cvm + CV_C2, gvm + GV_WZ2, gvm + GV_WP2);
                 ++acc_l2;
-                // E3: layer 3 + skip terms, layer 4, sigmoid (warps 0-3)
+                // E3: layer 3 + skip terms, layer 4 (each warp 64 of the 128 channels, four partial sums), sigmoid (warps 0-3)
                 ptx::mbar_wait(&bars->acc_full[ID_L3], acc_l3 & 1u, 23, prof);
                 ptx::tc_fence_after();
                 float logit = 0.0f;
-                if (e.hsel == 0) {
-                    logit = cvm[CV_C4] + gvm[GV_WZ4] * e.zf + (m == 1 ? gvm[GV_WP4] * e.pred : 0.0f);
-#pragma unroll 1
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t r[32];
-                        ptx::tmem_ld32(lane_l3 + q * 32, r);
-                        ptx::tmem_ld_wait();
+                {
+                    uint32_t r[2][32];
+                    const int cb = e.hsel * 64;
+                    ptx::tmem_ld32(lane_l3 + cb, r[0]);
+                    ptx::tmem_ld32(lane_l3 + cb + 32, r[1]);
+                    ptx::tmem_ld_wait();
+                    float lg[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const int c = q * 32 + 4 * j4;
+                            const int c = cb + q * 32 + 4 * j4;
                             const float4 a = *reinterpret_cast<const float4 *>(cvm + CV_C3 + c), z = *reinterpret_cast<const float4 *>(gvm + GV_WZ3 + c);
                             const float4 w4 = *reinterpret_cast<const float4 *>(gvm + GV_W4Y + c);
-                            float v0 = __uint_as_float(r[4 * j4]) + a.x + z.x * e.zf, v1 = __uint_as_float(r[4 * j4 + 1]) + a.y + z.y * e.zf;
-                            float v2 = __uint_as_float(r[4 * j4 + 2]) + a.z + z.z * e.zf, v3 = __uint_as_float(r[4 * j4 + 3]) + a.w + z.w * e.zf;
+                            float v0 = __uint_as_float(r[q][4 * j4]) + a.x + z.x * e.zf, v1 = __uint_as_float(r[q][4 * j4 + 1]) + a.y + z.y * e.zf;
+                            float v2 = __uint_as_float(r[q][4 * j4 + 2]) + a.z + z.z * e.zf, v3 = __uint_as_float(r[q][4 * j4 + 3]) + a.w + z.w * e.zf;
                             if (m == 1) {
                                 const float4 p = *reinterpret_cast<const float4 *>(gvm + GV_WP3 + c);
                                 v0 = fmaf(p.x, e.pred, v0); v1 = fmaf(p.y, e.pred, v1); v2 = fmaf(p.z, e.pred, v2); v3 = fmaf(p.w, e.pred, v3);
                             }
-                            logit = fmaf(w4.x, leaky(v0), logit); logit = fmaf(w4.y, leaky(v1), logit);
-                            logit = fmaf(w4.z, leaky(v2), logit); logit = fmaf(w4.w, leaky(v3), logit);
+                            lg[0] = fmaf(w4.x, leaky(v0), lg[0]); lg[1] = fmaf(w4.y, leaky(v1), lg[1]);
+                            lg[2] = fmaf(w4.z, leaky(v2), lg[2]); lg[3] = fmaf(w4.w, leaky(v3), lg[3]);
                         }
                     }
+                    logit = (lg[0] + lg[1]) + (lg[2] + lg[3]);
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -470,6 +473,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     if (P == 1) ptx::mbar_arrive(&bars->t1_free_b);
                 }
                 ++acc_l3;
+                // the upper half's partial sum goes to the quarter's lower warp (fixed order: lower + upper) through the
+                // row's pred_x cell: its last readers (the LR -> HR hand-over) are a whole pass of ring traffic behind
+                if (e.hsel == 1) pred_x[e.row] = logit;
+                asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+                if (e.hsel == 0) logit = (cvm[CV_C4] + gvm[GV_WZ4] * e.zf + (m == 1 ? gvm[GV_WP4] * e.pred : 0.0f)) + (logit + pred_x[e.row]);
                 if (e.hsel == 0) {
                     const float pred = pr.mask * (1.0f / (1.0f + expf(-logit)));
                     if (m == 0) {
