@@ -259,6 +259,12 @@ int surs_selftest_umma(surs_ctx *ctx, const float *A, const float *B, int N, int
  * D[256,N] = A[256,K] . B[N,K]^T, N multiple of 32 in [32,256], K <= 192. */
 int surs_selftest_umma2(surs_ctx *ctx, const float *A, const float *B, int N, int K, float *D, void *stream);
 
+/* Tensor-pipe rate probe (scripts/umma_rate.py): every issuing thread of a `grid`-CTA launch times
+ * reps x 4 MMAs of 128 x 256 x 16 (pair = 0, cta_group::1) or 256 x 256 x 16 (pair = 1, clusters of two CTAs,
+ * each holding half of the B operand); cycles[b] (device, `grid` entries) receives the clock cycles of CTA b's
+ * issuer (pair = 1: leaders only).  Measured on B200: 128.0 cycles per MMA in both modes. */
+int surs_selftest_umma_rate(surs_ctx *ctx, int pair, int grid, int reps, unsigned long long *cycles, void *stream);
+
 /* Counters for bench.py's "gpu_launches": kernels launched by this context so far. */
 int64_t surs_launch_count(const surs_ctx *ctx);
 

@@ -27,4 +27,7 @@ vols = ctx.eval_grid((res,) * 3, np.array([-0.5] * 3), np.array([0.5] * 3), case
                      plane_lo=0, plane_hi=planes)
 b.record()
 torch.cuda.synchronize()
-print("eval_grid %d^3 (%d planes) precision %s: %.2f ms" % (res, planes, sys.argv[2] if len(sys.argv) > 2 else "fp16", a.elapsed_time(b)))
+import hashlib
+
+sha = hashlib.sha256(b"".join(v.cpu().numpy().tobytes() for v in vols)).hexdigest()[:16]
+print("eval_grid %d^3 (%d planes) precision %s: %.2f ms  sha %s" % (res, planes, sys.argv[2] if len(sys.argv) > 2 else "fp16", a.elapsed_time(b), sha))

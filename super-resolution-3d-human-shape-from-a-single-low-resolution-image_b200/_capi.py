@@ -71,6 +71,7 @@ SIGNATURES = {
     "surs_save_obj_mesh": (ctypes.c_int, [ctypes.c_char_p, _P, _I64, _P, _I64]),
     "surs_selftest_umma": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P]),
     "surs_selftest_umma2": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int, _P, _P]),
+    "surs_selftest_umma_rate": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P]),
     "surs_launch_count": (_I64, [_P]),
 }
 
@@ -492,3 +493,13 @@ def selftest_umma2(ctx, A, B):
     with torch.cuda.device(ctx.device):
         ctx._check(ctx.lib.surs_selftest_umma2(ctx._h, _ptr(A), _ptr(B), B.shape[0], A.shape[1], _ptr(D), _stream(ctx.device)))
     return D
+
+
+def selftest_umma_rate(ctx, pair, grid, reps=1024):
+    """Cycles per MMA (128 x 256 x 16, or 256 x 256 x 16 on CTA pairs) seen by every issuing thread of a `grid`-CTA launch."""
+    out = torch.zeros(grid, dtype=torch.int64, device=ctx.device)
+    with torch.cuda.device(ctx.device):
+        ctx._check(ctx.lib.surs_selftest_umma_rate(ctx._h, int(bool(pair)), int(grid), int(reps), _ptr(out), _stream(ctx.device)))
+    torch.cuda.synchronize(ctx.device)
+    c = out.cpu().numpy()
+    return c[c > 0] / (4.0 * reps)

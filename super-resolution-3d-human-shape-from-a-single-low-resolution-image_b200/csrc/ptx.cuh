@@ -191,6 +191,36 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
     }
     if (prof) atomicAdd(prof + tag, (unsigned long long)(clock64() - t0));
 }
+// remote (or local) arrive that publishes this thread's prior writes cluster-wide
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// cluster-scope acquire wait that sleeps inside the instruction (same suspend hint as mbar_try_wait)
+__device__ __forceinline__ bool mbar_try_wait_cluster_hint(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster_hint(uint64_t *bar, uint32_t parity, int tag)
+{
+    if (mbar_try_wait_cluster_hint(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster_hint(bar, parity)) {
+        if ((++spins & 63u) == 0 && clock64() - t0 > 4000000000LL) {
+            printf("surs: cluster mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
 __device__ __forceinline__ void tmem_alloc2(uint32_t *smem_result, uint32_t cols)
 {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols) : "memory");

@@ -3,6 +3,8 @@
 // operand) and receives rows 128 r .. of D in its own TMEM; the leader CTA issues the MMAs for both.
 #include "tc_common.cuh"
 
+#include <string.h>
+
 namespace {
 
 using namespace tc;
@@ -86,6 +88,52 @@ umma2_selftest_kernel(const float *A, const float *B, int N, int K, float *D)
     if (warp == 0) ptx::tmem_dealloc2(tmem, 256);
 }
 
+// Issue-rate probe (scripts/umma_rate.py): `reps` x 4 MMAs (one 64-wide K block, N = 256) on zeroed operands,
+// cycles from first issue to the completion barrier.  pair = 1: cta_group::2 on a cluster of two CTAs (M = 256),
+// pair = 0: cta_group::1 in every CTA (M = 128).  All CTAs of the grid run the same loop concurrently.
+template <bool pair>
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int reps, unsigned long long *cycles)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (base - raw);
+    Bars2 *bars = reinterpret_cast<Bars2 *>(smem + A_BLK_BYTES + W_BLK_BYTES);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = pair ? ptx::cluster_ctarank() : 0;
+    for (int i = threadIdx.x; i < (A_BLK_BYTES + W_BLK_BYTES) / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(&bars->done, 1);
+        ptx::fence_barrier_init();
+    }
+    ptx::fence_proxy_async_smem();
+    if (pair) ptx::cluster_sync(); else __syncthreads();
+    if (warp == 0) { if (pair) ptx::tmem_alloc2(&bars->tmem_base, 512); else ptx::tmem_alloc(&bars->tmem_base, 512); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    if (pair) ptx::cluster_sync();
+    if (threadIdx.x == 0 && rank == 0) {
+        const uint64_t da = ptx::umma_desc_sw128(base), db = ptx::umma_desc_sw128(base + A_BLK_BYTES);
+        const uint32_t idesc = ptx::umma_idesc_f16(pair ? 256 : 128, 256);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r)
+            for (int k = 0; k < 4; ++k) {
+                if (pair) ptx::umma2_f16(tmem + (r & 1) * 256, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+                else ptx::umma_f16(tmem + (r & 1) * 256, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+            }
+        if (pair) ptx::umma2_commit(&bars->done, 0x3); else ptx::umma_commit(&bars->done);
+        ptx::mbar_wait_cluster(&bars->done, 0, 82);
+        cycles[blockIdx.x] = (unsigned long long)(clock64() - t0);
+    } else if (threadIdx.x == 0) {
+        ptx::mbar_wait_cluster(&bars->done, 0, 83);
+    }
+    ptx::tc_fence_before();
+    if (pair) ptx::cluster_sync(); else __syncthreads();
+    if (warp == 0) { if (pair) ptx::tmem_dealloc2(tmem, 512); else ptx::tmem_dealloc(tmem, 512); }
+}
+
 }  // namespace
 
 extern "C" int surs_selftest_umma2(surs_ctx *ctx, const float *A, const float *B, int N, int K, float *D, void *stream)
@@ -98,5 +146,31 @@ extern "C" int surs_selftest_umma2(surs_ctx *ctx, const float *A, const float *B
     SURS_CUDA(ctx, cudaFuncSetAttribute(umma2_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     umma2_selftest_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(A, B, N, K, D);
     SURS_LAUNCH_CHECK(ctx, "umma2_selftest_kernel");
+    return 0;
+}
+
+/* cycles[b] (leader CTAs / every CTA): clock cycles for reps x 4 MMAs of 128(256) x 256 x 16 */
+extern "C" int surs_selftest_umma_rate(surs_ctx *ctx, int pair, int grid, int reps, unsigned long long *cycles, void *stream)
+{
+    if (!ctx) return 1;
+    SURS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (grid < 1 || (pair && (grid & 1)) || reps < 1) SURS_FAIL(ctx, "surs_selftest_umma_rate: bad arguments");
+    const int smem = A_BLK_BYTES + W_BLK_BYTES + 64 + 1024;
+    SURS_CUDA(ctx, cudaFuncSetAttribute(umma_rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SURS_CUDA(ctx, cudaFuncSetAttribute(umma_rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pair ? 1 : 0;
+    if (pair) SURS_CUDA(ctx, cudaLaunchKernelEx(&cfg, umma_rate_kernel<true>, reps, cycles));
+    else SURS_CUDA(ctx, cudaLaunchKernelEx(&cfg, umma_rate_kernel<false>, reps, cycles));
+    SURS_LAUNCH_CHECK(ctx, "umma_rate_kernel");
     return 0;
 }

@@ -589,6 +589,45 @@ def test_incremental_layer1_dense_path(ctx, case32, monkeypatch):
             assert np.array_equal((a == 0).cpu().numpy(), (b == 0).cpu().numpy())
 
 
+def test_cta_pair_dense_kernel_is_bit_identical(ctx, case32, monkeypatch, capfd):
+    """SURS_COL_PAIR=1: the one-pass dense kernel on CTA pairs (query_col2.cu: tcgen05.mma.cta_group::2, each CTA holds
+    half of every weight block) -- same K order and accumulation, so the volumes are bit identical to the one-CTA
+    kernel, for even and odd tile counts, ragged columns and slabs; also under the refined default precision."""
+    from surs_b200 import _capi
+    for res, bmax in (((64, 64, 64), [0.5, 0.5, 0.5]), ((3, 5, 128), [0.5, 0.4, 0.55]), ((5, 9, 200), [0.5, 0.4, 0.55]), ((1, 1, 70), [0.2, 0.5, 0.5])):
+        args = (res, [-0.5] * 3, bmax, case32.calib) + znum(case32)
+        one = ctx.eval_grid(*args, precision=_capi.PREC_FP16)
+        ref = ctx.eval_grid(*args, precision=_capi.PREC_FP16R)
+        monkeypatch.setenv("SURS_COL_PAIR", "1")
+        pair = ctx.eval_grid(*args, precision=_capi.PREC_FP16)
+        pair_ref = ctx.eval_grid(*args, precision=_capi.PREC_FP16R)
+        slab = ctx.eval_grid(*args, precision=_capi.PREC_FP16, plane_lo=res[0] // 2, plane_hi=res[0])
+        monkeypatch.delenv("SURS_COL_PAIR")
+        for a, b, c, d, sl in zip(one, pair, ref, pair_ref, slab):
+            assert torch.equal(a, b), res
+            assert torch.equal(c, d), res
+            assert torch.equal(a[res[0] // 2:], sl), res
+    # the pair kernel really is what ran: its profiling switch reports from inside query_col2.cu
+    monkeypatch.setenv("SURS_COL_PAIR", "1")
+    monkeypatch.setenv("SURS_COL_ABLATE", "128")
+    capfd.readouterr()
+    ctx.eval_grid((4, 4, 128), [-0.5] * 3, [0.5] * 3, case32.calib, *znum(case32), precision=_capi.PREC_FP16)
+    monkeypatch.delenv("SURS_COL_ABLATE")
+    monkeypatch.delenv("SURS_COL_PAIR")
+    assert "[surs pair profile] pairs=8" in capfd.readouterr().err
+
+
+def test_tensor_pipe_rate_probe(ctx):
+    """scripts/umma_rate.py: one 128 x 256 x 16 MMA takes 128 cycles per SM with cta_group::1 and with cta_group::2
+    (each CTA holding half of B), with 2 CTAs and with all SMs busy."""
+    from surs_b200 import _capi
+    for pair in (0, 1):
+        for grid in (2, 148):
+            c = _capi.selftest_umma_rate(ctx, pair, grid, 1024)
+            assert len(c) == (grid // 2 if pair else grid)
+            assert 127.0 < c.min() and c.max() < 140.0, (pair, grid, c.min(), c.max())
+
+
 def test_marching_cubes_bitmask_word_boundaries(ctx):
     """Fast path (last axis % 4 == 0): rows that are not a multiple of 32 bits, surfaces crossing word
     boundaries, a single word per row, and the last cell of a row."""
