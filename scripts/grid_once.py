@@ -21,13 +21,22 @@ t = lambda a: torch.from_numpy(a).to(dev)
 ctx.set_weights([t(w) for w in case.mlp_lr[0]], [t(b) for b in case.mlp_lr[1]], [t(w) for w in case.mlp_hr[0]], [t(b) for b in case.mlp_hr[1]],
                 syn.MLP_DIM_LR, syn.MLP_DIM_HR, syn.RES_LAYERS)
 ctx.set_features(t(case.feat_lr), t(case.feat_hr))
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
-vols = ctx.eval_grid((res,) * 3, np.array([-0.5] * 3), np.array([0.5] * 3), case.calib, float(case.load_size // 2), float(case.z_size), precision=prec,
-                     plane_lo=0, plane_hi=planes)
-b.record()
-torch.cuda.synchronize()
+reps = int(os.environ.get("GRID_REPS", "1"))          # > 1: warm repeats, min / median reported (A/B runs: scripts/ab_grid.sh)
+times = []
+for _ in range(reps):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    vols = ctx.eval_grid((res,) * 3, np.array([-0.5] * 3), np.array([0.5] * 3), case.calib, float(case.load_size // 2), float(case.z_size), precision=prec,
+                         plane_lo=0, plane_hi=planes)
+    b.record()
+    torch.cuda.synchronize()
+    times.append(a.elapsed_time(b))
 import hashlib
 
 sha = hashlib.sha256(b"".join(v.cpu().numpy().tobytes() for v in vols)).hexdigest()[:16]
-print("eval_grid %d^3 (%d planes) precision %s: %.2f ms  sha %s" % (res, planes, sys.argv[2] if len(sys.argv) > 2 else "fp16", a.elapsed_time(b), sha))
+name = sys.argv[2] if len(sys.argv) > 2 else "fp16"
+if reps == 1:
+    print("eval_grid %d^3 (%d planes) precision %s: %.2f ms  sha %s" % (res, planes, name, times[0], sha))
+else:
+    print("eval_grid %d^3 (%d planes) precision %s: min %.2f median %.2f ms over %d warm calls (first %.2f)  sha %s" %
+          (res, planes, name, min(times[1:]), float(np.median(times[1:])), reps - 1, times[0], sha))

@@ -88,11 +88,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    # SURS_LIB: another build of the same library (A/B timing of kernel variants on one box: scripts/ab_grid.sh)
+    path = os.environ.get("SURS_LIB") or LIB_PATH
+    if not os.path.exists(path):
         raise RuntimeError(
             "libsurs.so not found at %s: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+            "(nvcc, sm_100a).  There is no CPU fallback." % path)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

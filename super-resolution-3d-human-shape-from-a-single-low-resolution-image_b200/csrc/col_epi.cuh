@@ -19,66 +19,71 @@ struct ColParams {
     int nmlp;                      // 2: both MLPs; 1: the LR MLP only (refinement of nodes only the LR surface depends on)
 };
 
-// 32 consecutive channels of one row -> fp16 -> A ring slot.  v = acc + add + wz * zf + wp * pred.
+// 32 consecutive channels of one row -> fp16 -> A ring slot.  v = ((add + wz * zf) + wp * pred) + acc, in packed
+// fp32 pairs (FFMA2 / FADD2: the same roundings as the scalar fmaf / + chain).
 template <int P, bool HAS_ACC, bool HAS_Z, bool HAS_P>
 __device__ __forceinline__ void finish32(const uint32_t *acc, const float *add, const float *wz, const float *wp,
                                          float zf, float pred, uint32_t dst, int row, int hsel, int part)
 {
+    const uint64_t zz = pk2(zf, zf), pp = pk2(pred, pred);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float v[8];
+        uint64_t v[4];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const float4 a = *reinterpret_cast<const float4 *>(add + 8 * j + 4 * q);
-            v[4 * q + 0] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+            v[2 * q] = pk2(a.x, a.y); v[2 * q + 1] = pk2(a.z, a.w);
             if (HAS_Z) {
                 const float4 z = *reinterpret_cast<const float4 *>(wz + 8 * j + 4 * q);
-                v[4 * q + 0] = fmaf(z.x, zf, v[4 * q + 0]); v[4 * q + 1] = fmaf(z.y, zf, v[4 * q + 1]);
-                v[4 * q + 2] = fmaf(z.z, zf, v[4 * q + 2]); v[4 * q + 3] = fmaf(z.w, zf, v[4 * q + 3]);
+                v[2 * q] = ffma2(pk2(z.x, z.y), zz, v[2 * q]); v[2 * q + 1] = ffma2(pk2(z.z, z.w), zz, v[2 * q + 1]);
             }
             if (HAS_P) {
                 const float4 p = *reinterpret_cast<const float4 *>(wp + 8 * j + 4 * q);
-                v[4 * q + 0] = fmaf(p.x, pred, v[4 * q + 0]); v[4 * q + 1] = fmaf(p.y, pred, v[4 * q + 1]);
-                v[4 * q + 2] = fmaf(p.z, pred, v[4 * q + 2]); v[4 * q + 3] = fmaf(p.w, pred, v[4 * q + 3]);
+                v[2 * q] = ffma2(pk2(p.x, p.y), pp, v[2 * q]); v[2 * q + 1] = ffma2(pk2(p.z, p.w), pp, v[2 * q + 1]);
             }
         }
         if (HAS_ACC) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += __uint_as_float(acc[8 * j + i]);
+            for (int i = 0; i < 4; ++i) v[i] = fadd2(v[i], pk2(__uint_as_float(acc[8 * j + 2 * i]), __uint_as_float(acc[8 * j + 2 * i + 1])));
         }
-        const uint4 o = make_uint4(act_h2<P>(v[0], v[1], part), act_h2<P>(v[2], v[3], part),
-                                   act_h2<P>(v[4], v[5], part), act_h2<P>(v[6], v[7], part));
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) up2(v[i], f[2 * i], f[2 * i + 1]);
+        const uint4 o = make_uint4(act_h2<P>(f[0], f[1], part), act_h2<P>(f[2], f[3], part),
+                                   act_h2<P>(f[4], f[5], part), act_h2<P>(f[6], f[7], part));
         st_shared_v4(dst + sw128_off(row, hsel * 4 + j), o);
     }
 }
 
 // Layer 0 for 8 channels (one 16-byte chunk) of 4 rows per lane: the per-channel constants are
-// loaded once for the four rows.  y0 = leaky(C0 + w_z z (+ w_p pred_lr)).
+// loaded once for the four rows.  y0 = leaky(C0 + w_z z (+ w_p pred_lr)), packed fp32 pairs.
 template <int P, bool HAS_P>
 __device__ __forceinline__ void produce8(const float *c0, const float *wz, const float *wp, const float (&zf)[4], const float (&pred)[4],
                                          uint32_t dst, int lane, int chunk, int part)
 {
-    float a[8], z[8], p[8];
+    uint64_t a[4], z[4], p[4];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const float4 av = *reinterpret_cast<const float4 *>(c0 + 4 * q), zv = *reinterpret_cast<const float4 *>(wz + 4 * q);
-        a[4 * q] = av.x; a[4 * q + 1] = av.y; a[4 * q + 2] = av.z; a[4 * q + 3] = av.w;
-        z[4 * q] = zv.x; z[4 * q + 1] = zv.y; z[4 * q + 2] = zv.z; z[4 * q + 3] = zv.w;
+        a[2 * q] = pk2(av.x, av.y); a[2 * q + 1] = pk2(av.z, av.w);
+        z[2 * q] = pk2(zv.x, zv.y); z[2 * q + 1] = pk2(zv.z, zv.w);
         if (HAS_P) {
             const float4 pv = *reinterpret_cast<const float4 *>(wp + 4 * q);
-            p[4 * q] = pv.x; p[4 * q + 1] = pv.y; p[4 * q + 2] = pv.z; p[4 * q + 3] = pv.w;
+            p[2 * q] = pk2(pv.x, pv.y); p[2 * q + 1] = pk2(pv.z, pv.w);
         }
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        float v[8];
+        const uint64_t zz = pk2(zf[r], zf[r]), pp = pk2(pred[r], pred[r]);
+        float f[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            v[i] = fmaf(z[i], zf[r], a[i]);
-            if (HAS_P) v[i] = fmaf(p[i], pred[r], v[i]);
+        for (int i = 0; i < 4; ++i) {
+            uint64_t v = ffma2(z[i], zz, a[i]);
+            if (HAS_P) v = ffma2(p[i], pp, v);
+            up2(v, f[2 * i], f[2 * i + 1]);
         }
-        const uint4 o = make_uint4(act_h2<P>(v[0], v[1], part), act_h2<P>(v[2], v[3], part),
-                                   act_h2<P>(v[4], v[5], part), act_h2<P>(v[6], v[7], part));
+        const uint4 o = make_uint4(act_h2<P>(f[0], f[1], part), act_h2<P>(f[2], f[3], part),
+                                   act_h2<P>(f[4], f[5], part), act_h2<P>(f[6], f[7], part));
         st_shared_v4(dst + sw128_off(lane + 32 * r, chunk), o);
     }
 }

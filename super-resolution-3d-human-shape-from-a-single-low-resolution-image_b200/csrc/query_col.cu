@@ -89,27 +89,29 @@ template <int P, bool HAS_P>
 __device__ __forceinline__ void produce8x(const C0Rows &c0, const float *wz, const float *wp, const float (&zf)[4], const float (&pred)[4],
                                           uint32_t dst, int lane, int chunk, int part)
 {
-    float z[8], p[8];
+    uint64_t z[4], p[4];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const float4 zv = *reinterpret_cast<const float4 *>(wz + 4 * q);
-        z[4 * q] = zv.x; z[4 * q + 1] = zv.y; z[4 * q + 2] = zv.z; z[4 * q + 3] = zv.w;
+        z[2 * q] = pk2(zv.x, zv.y); z[2 * q + 1] = pk2(zv.z, zv.w);
         if (HAS_P) {
             const float4 pv = *reinterpret_cast<const float4 *>(wp + 4 * q);
-            p[4 * q] = pv.x; p[4 * q + 1] = pv.y; p[4 * q + 2] = pv.z; p[4 * q + 3] = pv.w;
+            p[2 * q] = pk2(pv.x, pv.y); p[2 * q + 1] = pk2(pv.z, pv.w);
         }
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const float a[8] = {c0.v[r][0].x, c0.v[r][0].y, c0.v[r][0].z, c0.v[r][0].w, c0.v[r][1].x, c0.v[r][1].y, c0.v[r][1].z, c0.v[r][1].w};
-        float v[8];
+        const uint64_t a[4] = {pk2(c0.v[r][0].x, c0.v[r][0].y), pk2(c0.v[r][0].z, c0.v[r][0].w), pk2(c0.v[r][1].x, c0.v[r][1].y), pk2(c0.v[r][1].z, c0.v[r][1].w)};
+        const uint64_t zz = pk2(zf[r], zf[r]), pp = pk2(pred[r], pred[r]);
+        float f[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            v[i] = fmaf(z[i], zf[r], a[i]);
-            if (HAS_P) v[i] = fmaf(p[i], pred[r], v[i]);
+        for (int i = 0; i < 4; ++i) {
+            uint64_t v = ffma2(z[i], zz, a[i]);
+            if (HAS_P) v = ffma2(p[i], pp, v);
+            up2(v, f[2 * i], f[2 * i + 1]);
         }
-        const uint4 o = make_uint4(act_h2<P>(v[0], v[1], part), act_h2<P>(v[2], v[3], part),
-                                   act_h2<P>(v[4], v[5], part), act_h2<P>(v[6], v[7], part));
+        const uint4 o = make_uint4(act_h2<P>(f[0], f[1], part), act_h2<P>(f[2], f[3], part),
+                                   act_h2<P>(f[4], f[5], part), act_h2<P>(f[6], f[7], part));
         st_shared_v4(dst + sw128_off(lane + 32 * r, chunk), o);
     }
 }
@@ -369,7 +371,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                     ptx::tmem_ld32(lane_l3 + cb, r[0]);
                     ptx::tmem_ld32(lane_l3 + cb + 32, r[1]);
                     ptx::tmem_ld_wait();
-                    float lg[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    // packed fp32 pairs: v = ((acc + C3) + wz3 z) (+ wp3 pred), partial sums (lg0, lg1) and (lg2, lg3)
+                    uint64_t lg01 = pk2(0.0f, 0.0f), lg23 = lg01;
+                    const uint64_t zz = pk2(e.zf, e.zf), pp = pk2(e.pred, e.pred), slope = pk2(SURS_LEAKY, SURS_LEAKY);
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
 #pragma unroll
@@ -377,16 +381,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) query_col_kernel(const __grid_con
                             const int c = cb + q * 32 + 4 * j4;
                             const float4 a = *reinterpret_cast<const float4 *>(cvm + CV_C3 + c), z = *reinterpret_cast<const float4 *>(gvm + GV_WZ3 + c);
                             const float4 w4 = *reinterpret_cast<const float4 *>(gvm + GV_W4Y + c);
-                            float v0 = __uint_as_float(r[q][4 * j4]) + a.x + z.x * e.zf, v1 = __uint_as_float(r[q][4 * j4 + 1]) + a.y + z.y * e.zf;
-                            float v2 = __uint_as_float(r[q][4 * j4 + 2]) + a.z + z.z * e.zf, v3 = __uint_as_float(r[q][4 * j4 + 3]) + a.w + z.w * e.zf;
+                            uint64_t v01 = fadd2(pk2(__uint_as_float(r[q][4 * j4]), __uint_as_float(r[q][4 * j4 + 1])), pk2(a.x, a.y));
+                            uint64_t v23 = fadd2(pk2(__uint_as_float(r[q][4 * j4 + 2]), __uint_as_float(r[q][4 * j4 + 3])), pk2(a.z, a.w));
+                            v01 = ffma2(pk2(z.x, z.y), zz, v01);
+                            v23 = ffma2(pk2(z.z, z.w), zz, v23);
                             if (m == 1) {
                                 const float4 p = *reinterpret_cast<const float4 *>(gvm + GV_WP3 + c);
-                                v0 = fmaf(p.x, e.pred, v0); v1 = fmaf(p.y, e.pred, v1); v2 = fmaf(p.z, e.pred, v2); v3 = fmaf(p.w, e.pred, v3);
+                                v01 = ffma2(pk2(p.x, p.y), pp, v01);
+                                v23 = ffma2(pk2(p.z, p.w), pp, v23);
                             }
-                            lg[0] = fmaf(w4.x, leaky(v0), lg[0]); lg[1] = fmaf(w4.y, leaky(v1), lg[1]);
-                            lg[2] = fmaf(w4.z, leaky(v2), lg[2]); lg[3] = fmaf(w4.w, leaky(v3), lg[3]);
+                            float v0, v1, v2, v3, s0, s1, s2, s3;
+                            up2(v01, v0, v1); up2(v23, v2, v3);
+                            up2(fmul2(v01, slope), s0, s1); up2(fmul2(v23, slope), s2, s3);
+                            lg01 = ffma2(pk2(w4.x, w4.y), pk2(fmaxf(v0, s0), fmaxf(v1, s1)), lg01);
+                            lg23 = ffma2(pk2(w4.z, w4.w), pk2(fmaxf(v2, s2), fmaxf(v3, s3)), lg23);
                         }
                     }
+                    float lg[4];
+                    up2(lg01, lg[0], lg[1]); up2(lg23, lg[2], lg[3]);
                     logit = (lg[0] + lg[1]) + (lg[2] + lg[3]);
                 }
                 ptx::tc_fence_before();

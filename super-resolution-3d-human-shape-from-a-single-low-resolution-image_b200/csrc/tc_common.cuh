@@ -55,6 +55,34 @@ __device__ __forceinline__ uint32_t act_h2(float a, float b, int part)
     return split_h2(leaky(a), leaky(b), part);
 }
 
+// Packed fp32 pairs (sm_100: FFMA2 / FADD2): per element exactly fma.rn / add.rn, half the instructions on the FMA pipe
+// that bounds the epilogue side of the column kernels.
+__device__ __forceinline__ uint64_t pk2(float a, float b)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void up2(uint64_t r, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b)
+{
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b)
+{
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v)
 {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
