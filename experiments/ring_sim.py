@@ -6,7 +6,8 @@ import sys
 
 NG = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 NSLOT = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-TILES = 40
+TILES = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+SEEDS = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 WPG = 8
 
 
@@ -163,8 +164,9 @@ def run(seed):
 
 
 ok = True
-for seed in range(5):
+for seed in range(SEEDS):
     for b in a_ready + a_ready_b + a_free + acc_full + acc_free + [t1_free_b, sync1]:
         b.phase, b.pending = 0, b.count
     ok = run(seed) and ok
 print("NG=%d NSLOT=%d:" % (NG, NSLOT), "all runs completed" if ok else "FAILED")
+sys.exit(0 if ok else 1)
